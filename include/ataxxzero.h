@@ -1,0 +1,98 @@
+/*
+ * ataxxzero.h -- C ABI of libataxxzero.so, the B200-native self-play hot path.
+ *
+ * Plain pointers and sizes only (no torch / C++ types).  Every entry point cites the
+ * reference interface it replaces (file:line relative to petersn/AtaxxZero).  All
+ * functions return AZ_OK (0) or a negative az_status; az_last_error() gives the text.
+ * There is NO CPU fallback: without a usable sm_100 device every compute call fails
+ * with AZ_ERR_CUDA.  "Host" pointers are ordinary (ideally pinned) host memory;
+ * "dev" pointers are device memory on the context's GPU (e.g. torch tensor data_ptr()).
+ */
+#ifndef ATAXXZERO_H
+#define ATAXXZERO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    AZ_OK = 0,
+    AZ_ERR_ARG = -1,        /* bad argument (null pointer, size, FEN, ...)           */
+    AZ_ERR_CUDA = -2,       /* CUDA runtime / no device / kernel failure             */
+    AZ_ERR_STATE = -3,      /* call made in the wrong state (e.g. no weights loaded) */
+    AZ_ERR_CAPACITY = -4,   /* a device pool overflowed (node pool, record buffer)   */
+    AZ_ERR_IO = -5          /* output file could not be opened / written             */
+} az_status;
+
+/* cpp/ataxx.hpp:28-34 `struct Position` -- identical layout (32 bytes).
+ * bit sq = rank*7 + file, a1 = 0 ... g7 = 48; turn 0 = x (CROSS), 1 = o (NOUGHT). */
+typedef struct {
+    int32_t  ply;
+    int32_t  turn;
+    uint64_t blockers;
+    uint64_t pieces[2];
+} az_position;
+
+/* cpp/move.hpp:9-31 `struct Move{int from,to}` packed as from | to<<8; a single (clone)
+ * move has from == to (move.cpp:100-103); AZ_NO_MOVE mirrors NO_MOVE={50,50} (move.hpp:33). */
+typedef uint16_t az_move;
+#define AZ_MOVE(from, to)  ((az_move)((from) | ((to) << 8)))
+#define AZ_MOVE_FROM(m)    ((int)((m) & 0xff))
+#define AZ_MOVE_TO(m)      ((int)((m) >> 8))
+#define AZ_NO_MOVE         AZ_MOVE(50, 50)
+#define AZ_MAX_MOVES       256          /* movegen.cpp:69 asserts n < 256 */
+#define AZ_FEATURES        196          /* [7][7][4]  index 28x+4y+c  (self_play_client.cpp:174-202) */
+#define AZ_LOGITS          833          /* [7][7][17] index 119x+17y+p (self_play_client.cpp:224-237) */
+
+typedef struct az_context az_context;
+
+/* ---------------- context ---------------- */
+const char *az_last_error(void);                       /* thread-local message of the last failure */
+const char *az_version(void);
+int az_create(int device, uint64_t seed, az_context **out);   /* replaces the process-global state of
+                                                                  self_play_client.cpp:591-602 */
+void az_destroy(az_context *ctx);
+int az_device_count(void);
+int az_sync(az_context *ctx);                          /* cudaStreamSynchronize on the context stream */
+/* raw handle of the context's stream (cudaStream_t) so callers can record CUDA events on it */
+void *az_stream(az_context *ctx);
+
+/* ---------------- rules: host-side helpers (no GPU) ---------------- */
+/* cpp/ataxx.cpp:14-92 set_board: same FEN grammar, "startpos", same return codes 0..8 */
+int az_set_board(az_position *pos, const char *fen);
+/* cpp/move.cpp:11-21 move_string: "b6" for singles, "a7b5" for doubles; returns length */
+int az_move_string(az_move m, char out[5]);
+/* inverse of move_string (cpp/makemove.cpp:22-54 parser); returns AZ_NO_MOVE on bad text */
+az_move az_parse_move(const char *text);
+/* fen text of a position (rows rank 7..1, '-' blockers); returns length */
+int az_fen(const az_position *pos, char *out, size_t cap);
+
+/* ---------------- rules: batched device kernels (host buffers in/out) ---------------- */
+/* cpp/movegen.cpp:10-79 movegen over n positions.  moves is [n][AZ_MAX_MOVES]; order is the
+ * reference's (doubles by from/to ascending, then singles by destination ascending). */
+int az_movegen_batch(az_context *ctx, const az_position *pos, int n, az_move *moves, int32_t *counts);
+/* cpp/makemove.cpp:56-76 makemove, one move per position, in place */
+int az_makemove_batch(az_context *ctx, az_position *pos, const az_move *moves, int n);
+/* cpp/self_play_client.cpp:109-144 get_board_result: 0 ongoing, 1 x wins, 2 o wins */
+int az_result_batch(az_context *ctx, const az_position *pos, int n, int32_t *result);
+/* cpp/self_play_client.cpp:174-202 feature planes, float [n][7][7][4] */
+int az_features_batch(az_context *ctx, const az_position *pos, int n, float *features);
+/* cpp/bitboards.cpp:6-39 whole-board dilations */
+int az_jump_bb_batch(az_context *ctx, const uint64_t *bb, int n, uint64_t *single_out, uint64_t *double_out);
+
+/* ---------------- perft (perft.py:5-26; reference C++ has only movegen+makemove) ------------- */
+/* nodes[i] = number of leaf nodes at `depth` below pos[i] (a stuck side has 0 children) */
+int az_perft_batch(az_context *ctx, const az_position *pos, int n, int depth, uint64_t *nodes);
+int az_perft(az_context *ctx, const az_position *root, int depth, uint64_t *nodes);
+/* device-resident variant: d_pos / d_nodes are device pointers; runs on the context stream */
+int az_perft_batch_dev(az_context *ctx, const void *d_pos, int n, int depth, void *d_nodes);
+/* statistics of the last perft call: device-side counted parents ("count nodes") and kernel launches */
+int az_perft_last_stats(az_context *ctx, uint64_t *count_nodes, int32_t *launches, int32_t *frontier_items);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
