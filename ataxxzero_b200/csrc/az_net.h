@@ -1,0 +1,32 @@
+// az_net.h -- device-resident network weights (internal).
+#pragma once
+#include "az_common.h"
+#include <cuda_bf16.h>
+
+constexpr int AZ_F = 128;            // filters (model.py:16)
+constexpr float AZ_BN_EPS = 1e-3f;   // tf.layers.batch_normalization default epsilon
+
+struct AzNet {
+    int filters = 0, blocks = 0, layers = 0;   // layers = 1 + 2*blocks convolutions with batch-norm
+    // fp32 mode: weights in TF order [layer][tap = kh*3+kw][cin][cout]; layer 0 has cin = 4
+    float *w_in = nullptr;       // [9][4][F]
+    float *w_tower = nullptr;    // [2*blocks][9][F][F]
+    float *bn_mean = nullptr;    // [layers][F]
+    float *bn_scale = nullptr;   // [layers][F]   1/sqrt(var + eps)
+    float *w_policy = nullptr;   // [F][17]
+    float *w_value = nullptr;    // [F]
+    float *fc_w = nullptr;       // [49]
+    float *fc_b = nullptr;       // [1]
+    // bf16 tensor-core mode (az_net_tc.cu): BN scale folded into the weights, UMMA operand layout
+    __nv_bfloat16 *tc_w = nullptr;     // [2*blocks][18 chunks][8 kgroups][128 cout][8 cin]
+    float *tc_shift = nullptr;         // [layers][F]   -mean * scale
+    __nv_bfloat16 *tc_w_in = nullptr;  // [5 k-steps][2 k-groups = taps][128 cout][8 cin (4 real)] bf16, scale folded
+    __nv_bfloat16 *tc_w_heads = nullptr; // [16 k-groups][32 rows: 17 policy + 1 value + pad][8 cin] bf16
+};
+
+// az_net_tc.cu
+int az_net_tc_prepare(az_context *ctx, AzNet *net, const std::vector<float> &host_packed);
+int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values);
+void az_net_tc_release(AzNet *net);
+
+enum { AZ_IN_F32 = 0, AZ_IN_POS = 1 };

@@ -1,0 +1,588 @@
+// az_net_tc.cu -- the conv tower as bf16 tcgen05 implicit GEMMs, whole network in ONE persistent
+// kernel (sm_100a).  Replaces TF1's sess.run of model.py:38-79 on the self-play hot path
+// (accelerated_generate_games.py:57-63) and the dead cuDNN stub cpp/fast_eval.cpp:37-126.
+//
+// Mapping (DESIGN.md "net kernel"):
+//   * A CTA owns a "unit" of 4 boards = 2 M-tiles of 128 GEMM rows.  A board is 64 rows: row
+//     8 + 8x + y holds cell (x, y), y == 7 and rows 0..7 are zero padding, so each 3x3 tap is a
+//     CONSTANT ROW SHIFT (8*dx + dy) of the same activation buffer -> the im2col matrix is never
+//     built; the A-operand descriptor of a tap just starts `shift` rows earlier/later.
+//   * Activations stay in shared memory for all 25 layers as bf16 in the no-swizzle K-major UMMA
+//     layout [k-group of 8 channels][row][8 channels] (16-byte rows, so any row shift is a legal
+//     descriptor start address).  Outputs overwrite inputs in place: an epilogue only runs after
+//     every MMA of its layer has completed.
+//   * Accumulators (128 lanes x 128 fp32 columns per tile) and the fp32 residual stream live in
+//     TMEM: 2 tiles x (128 + 128) columns = all 512.
+//   * Weights (BN scale folded, bf16) are pre-tiled in HBM in exactly the shared-memory image of a
+//     pipeline stage (one tap x 64 input channels = 16 KiB) and streamed through a 4-stage ring by
+//     1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx); each stage feeds both tiles.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (single elected lane), warps 2-5 /
+//     6-9 = epilogue of tile 0 / tile 1 (TMEM -> +shift, +residual, ReLU -> bf16 -> smem, and the
+//     heads' logits/value to HBM).
+#include "az_net.h"
+#include "az_rules.cuh"
+
+namespace {
+
+constexpr int F = AZ_F;                  // channels
+constexpr int KG = F / 8;                // 16 k-groups of 8 channels
+constexpr int TILE_M = 128;              // GEMM rows per tile (2 boards x 64)
+constexpr int TILES = 2;                 // tiles per CTA unit
+constexpr int UNIT_BOARDS = 2 * TILES;   // 4
+constexpr int MARGIN = 16;               // zero rows before/after the tiles (shifts reach +-9)
+constexpr int ACT_ROWS = MARGIN + TILES * TILE_M + MARGIN;     // 288
+constexpr int ROW_BYTES = 16;            // 8 bf16
+constexpr int ACT_LBO = ACT_ROWS * ROW_BYTES;                  // bytes between k-groups of the A operand
+constexpr int ACT_BYTES = KG * ACT_LBO;                        // 73728
+constexpr int STAGES = 4;
+constexpr int STAGE_BYTES = 8 * F * ROW_BYTES;                 // 8 k-groups x 128 cout x 16 B = 16384
+constexpr int CHUNKS = 18;               // per layer: 2 input-channel halves x 9 taps
+constexpr int W_LBO = F * ROW_BYTES;     // 2048: bytes between k-groups of the B operand
+constexpr int IN_BYTES = ACT_ROWS * ROW_BYTES;                 // input planes: one k-group (4 real + 4 zero channels)
+constexpr int ZERO_BYTES = TILE_M * ROW_BYTES;                 // zero k-group for the padded 10th tap
+constexpr int WIN_BYTES = 5 * 2 * F * ROW_BYTES;               // input conv: 5 k-steps x 2 k-groups x 128 cout
+constexpr int HEAD_N = 32;               // 17 policy planes + 1 value plane, padded to a legal UMMA N
+constexpr int WHEAD_BYTES = KG * HEAD_N * ROW_BYTES;           // 8192
+constexpr int HEAD_LBO = HEAD_N * ROW_BYTES;
+
+// shared memory map (bytes)
+constexpr int OFF_ACT = 0;
+constexpr int OFF_RING = OFF_ACT + ACT_BYTES;
+constexpr int OFF_IN = OFF_RING + STAGES * STAGE_BYTES;
+constexpr int OFF_ZERO = OFF_IN + IN_BYTES;
+constexpr int OFF_WIN = OFF_ZERO + ZERO_BYTES;
+constexpr int OFF_WHEAD = OFF_WIN + WIN_BYTES;
+constexpr int OFF_SHIFT = OFF_WHEAD + WHEAD_BYTES;             // float[TILES][2][F]: per-layer BN shifts, double-buffered
+constexpr int OFF_VPART = OFF_SHIFT + TILES * 2 * F * 4;       // float[TILES][4] value-head partial sums
+constexpr int OFF_BAR = OFF_VPART + 64;
+constexpr int NUM_BARS = 2 * STAGES + 2 * TILES + 2;           // full/empty ring, acc_full/act_ready per tile, const loads
+constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16;
+static_assert(SMEM_BYTES < 227 * 1024, "shared memory budget");
+
+constexpr int NUM_WARPS = 2 + 4 * TILES;     // 10
+constexpr int NUM_THREADS = NUM_WARPS * 32;  // 320
+
+// TMEM columns
+constexpr uint32_t TM_ACC = 0;               // + tile*128
+constexpr uint32_t TM_RES = 256;             // + tile*128
+
+// instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N
+constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24); }
+constexpr uint32_t IDESC_128 = make_idesc(128);
+constexpr uint32_t IDESC_HEAD = make_idesc(HEAD_N);
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// no-swizzle K-major shared-memory matrix descriptor (SBO = 128 B: 8-row core matrices are contiguous)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)(128 >> 4) << 32) | (1ULL << 46);
+}
+
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+// named barrier among the 4 epilogue warps of one tile
+__device__ __forceinline__ void group_sync(int tile) { asm volatile("bar.sync %0, 128;" ::"r"(1 + tile) : "memory"); }
+
+struct TcParams {
+    const void *input;                 // float[n][196] or az_position[n]
+    int n;                             // boards
+    int layers;                        // 1 + 2*blocks
+    int debug_layers;                  // >= 0: stop after this many conv layers and dump activations
+    const __nv_bfloat16 *w_tower;      // [2*blocks][18][8][128][8]
+    const __nv_bfloat16 *w_in;         // [5][2][128][8]
+    const __nv_bfloat16 *w_heads;      // [16][32][8]
+    const float *shift;                // [layers][128]
+    const float *fc_w;                 // [49]
+    const float *fc_b;                 // [1]
+    float *logits;                     // [n][833]
+    float *values;                     // [n]
+    float *debug_act;                  // [n][49][128] (debug only)
+};
+
+// row r of a tile -> board within tile / cell; real rows carry data, the rest are zero padding
+__device__ __forceinline__ bool row_is_real(int r, int &board_in_tile, int &cell)
+{
+    board_in_tile = r >> 6;
+    const int w = r & 63;
+    const int x = (w >> 3) - 1, y = w & 7;
+    cell = x * 7 + y;
+    return w >= 8 && y != 7;
+}
+
+template <int IN_KIND>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto bar = [&](int i) { return sbase + OFF_BAR + 8 * i; };
+    // barrier indices
+    const int B_FULL = 0, B_EMPTY = STAGES, B_ACC = 2 * STAGES, B_ACT = 2 * STAGES + TILES, B_CONST = 2 * STAGES + 2 * TILES;
+    const int B_IN = B_CONST + 1;      // input planes staged (arrived by the epilogue threads)
+
+    const int num_units = (P.n + UNIT_BOARDS - 1) / UNIT_BOARDS;
+    const int tower_layers = P.layers - 1;          // tensor-core 128->128 convs
+    const int run_layers = P.debug_layers >= 0 ? min(P.debug_layers, P.layers) : P.layers;   // conv layers executed (incl. input conv)
+
+    // ---- one-time setup ----
+    for (int i = threadIdx.x; i < (ACT_BYTES + 0) / 16; i += NUM_THREADS) reinterpret_cast<uint4 *>(smem + OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (IN_BYTES + ZERO_BYTES) / 16; i += NUM_THREADS)
+        reinterpret_cast<uint4 *>(smem + OFF_IN)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
+        for (int t = 0; t < TILES; ++t) { mbar_init(bar(B_ACC + t), 1); mbar_init(bar(B_ACT + t), 128); }
+        mbar_init(bar(B_CONST), 1);
+        mbar_init(bar(B_IN), 128 * TILES);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(sbase + OFF_TMEM, 512);
+    fence_proxy_async();                 // zero-fills above must be visible to the tensor core's async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + OFF_TMEM);
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            mbar_expect_tx(bar(B_CONST), WIN_BYTES + WHEAD_BYTES);
+            bulk_g2s(sbase + OFF_WIN, P.w_in, WIN_BYTES, bar(B_CONST));
+            bulk_g2s(sbase + OFF_WHEAD, P.w_heads, WHEAD_BYTES, bar(B_CONST));
+            uint32_t it = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int nl = min(tower_layers, run_layers - 1);
+                for (int l = 0; l < nl; ++l) {
+                    const uint8_t *src = reinterpret_cast<const uint8_t *>(P.w_tower) + (size_t)l * CHUNKS * STAGE_BYTES;
+                    for (int c = 0; c < CHUNKS; ++c, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait(bar(B_EMPTY + s), ((it / STAGES) & 1) ^ 1);
+                        mbar_expect_tx(bar(B_FULL + s), STAGE_BYTES);
+                        bulk_g2s(sbase + OFF_RING + s * STAGE_BYTES, src + (size_t)c * STAGE_BYTES, STAGE_BYTES, bar(B_FULL + s));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            mbar_wait(bar(B_CONST), 0);
+            uint32_t it = 0, in_phase = 0, act_phase = 0;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                // ---- input conv: 9 taps x 8 (4 real) channels, two taps per K=16 step ----
+                mbar_wait(bar(B_IN), in_phase);
+                in_phase ^= 1;
+                tc_fence_after();
+                if (run_layers >= 1) {
+                    for (int t = 0; t < TILES; ++t) {
+                        const uint32_t in_rows = sbase + OFF_IN + (MARGIN + t * TILE_M) * ROW_BYTES;
+                        for (int j = 0; j < 5; ++j) {
+                            const int tap0 = 2 * j, tap1 = 2 * j + 1;
+                            const int sh0 = (tap0 / 3 - 1) * 8 + (tap0 % 3 - 1);
+                            const uint32_t a0 = in_rows + sh0 * ROW_BYTES;
+                            uint32_t a1;
+                            if (tap1 < 9) a1 = in_rows + ((tap1 / 3 - 1) * 8 + (tap1 % 3 - 1)) * ROW_BYTES;
+                            else a1 = sbase + OFF_ZERO;
+                            const uint64_t ad = make_desc(a0, a1 - a0);
+                            const uint64_t bd = make_desc(sbase + OFF_WIN + j * 2 * W_LBO, W_LBO);
+                            umma(tmem_base + TM_ACC + t * 128, ad, bd, IDESC_128, j > 0);
+                        }
+                        umma_commit(bar(B_ACC + t));
+                    }
+                }
+                // ---- tower ----
+                const int nl = min(tower_layers, run_layers - 1);
+                for (int l = 0; l < nl; ++l) {
+                    for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + t), act_phase);
+                    act_phase ^= 1;
+                    tc_fence_after();
+                    for (int c = 0; c < CHUNKS; ++c, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait(bar(B_FULL + s), (it / STAGES) & 1);
+                        tc_fence_after();
+                        const int half = c / 9, tap = c % 9;
+                        const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
+                        for (int t = 0; t < TILES; ++t) {
+                            const uint32_t a_rows = sbase + OFF_ACT + (MARGIN + t * TILE_M + shift) * ROW_BYTES + half * 8 * ACT_LBO;
+                            const uint32_t b_rows = sbase + OFF_RING + s * STAGE_BYTES;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint64_t ad = make_desc(a_rows + 2 * j * ACT_LBO, ACT_LBO);
+                                const uint64_t bd = make_desc(b_rows + 2 * j * W_LBO, W_LBO);
+                                umma(tmem_base + TM_ACC + t * 128, ad, bd, IDESC_128, (c | j) != 0);
+                            }
+                        }
+                        umma_commit(bar(B_EMPTY + s));
+                    }
+                    for (int t = 0; t < TILES; ++t) umma_commit(bar(B_ACC + t));
+                }
+                // ---- heads: [128 rows x 128 ch] x [128 ch x 32] ----
+                for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + t), act_phase);
+                act_phase ^= 1;
+                tc_fence_after();
+                if (P.debug_layers < 0) {
+                    for (int t = 0; t < TILES; ++t) {
+                        const uint32_t a_rows = sbase + OFF_ACT + (MARGIN + t * TILE_M) * ROW_BYTES;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint64_t ad = make_desc(a_rows + 2 * j * ACT_LBO, ACT_LBO);
+                            const uint64_t bd = make_desc(sbase + OFF_WHEAD + 2 * j * HEAD_LBO, HEAD_LBO);
+                            umma(tmem_base + TM_ACC + t * 128, ad, bd, IDESC_HEAD, j > 0);
+                        }
+                        umma_commit(bar(B_ACC + t));
+                    }
+                }
+                // the next unit's input planes may only be consumed after its epilogue threads re-stage them,
+                // which they do after finishing this unit (B_IN handshake above).
+            }
+        }
+    } else {
+        // =============================== epilogue warps ===============================
+        const int tile = (warp - 2) >> 2;
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may touch
+        const int r = quad * 32 + lane;               // row within the tile == TMEM lane
+        const int gtid = (warp - 2 - tile * 4) * 32 + lane;   // 0..127 within the tile's epilogue group
+        int bit, cell;
+        const bool real = row_is_real(r, bit, cell);
+        float *shift_base = reinterpret_cast<float *>(smem + OFF_SHIFT) + tile * 2 * F;
+        float *vpart = reinterpret_cast<float *>(smem + OFF_VPART) + tile * 4;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        uint8_t *act_row = smem + OFF_ACT + (MARGIN + tile * TILE_M + r) * ROW_BYTES;
+        uint32_t acc_phase = 0;
+
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            const int board = unit * UNIT_BOARDS + tile * 2 + bit;
+            const bool live = real && board < P.n;
+            // ---- stage the input planes of this row: 4 feature channels + 4 zeros, bf16 ----
+            {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (live) {
+                    float f[4];
+                    if (IN_KIND == AZ_IN_F32) {
+                        const float4 q = reinterpret_cast<const float4 *>(P.input)[(size_t)board * 49 + cell];
+                        f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
+                    } else {
+                        az_position p = reinterpret_cast<const az_position *>(P.input)[board];
+                        p.turn &= 1;
+                        az::feature_cell(p, cell / 7, cell % 7, f);
+                    }
+                    v.x = pack_bf16(f[0], f[1]);
+                    v.y = pack_bf16(f[2], f[3]);
+                }
+                *reinterpret_cast<uint4 *>(smem + OFF_IN + (MARGIN + tile * TILE_M + r) * ROW_BYTES) = v;
+                fence_proxy_async();
+                mbar_arrive(bar(B_IN));
+            }
+            for (int l = 0; l < run_layers; ++l) {
+                // layer l: 0 = input conv, odd = first conv of a block, even (>0) = second conv (+residual)
+                const bool second = l > 0 && (l & 1) == 0;
+                const bool writes_res = l == 0 || second;
+                float *shift_s = shift_base + (l & 1) * F;     // double-buffered: a fast thread may run one layer ahead
+                shift_s[gtid] = __ldg(P.shift + l * F + gtid);
+                group_sync(tile);
+                mbar_wait(bar(B_ACC + tile), acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {          // 32 channels at a time
+                    uint32_t a[32];
+                    tmem_ld32(lane_addr + TM_ACC + tile * 128 + q * 32, a);
+                    uint32_t res[32];
+                    if (second) tmem_ld32(lane_addr + TM_RES + tile * 128 + q * 32, res);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float v = __uint_as_float(a[i]) + shift_s[q * 32 + i];
+                        if (second) v += __uint_as_float(res[i]);
+                        v = live ? fmaxf(v, 0.f) : 0.f;
+                        a[i] = __float_as_uint(v);
+                    }
+                    if (writes_res) tmem_st32(lane_addr + TM_RES + tile * 128 + q * 32, a);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(a[8 * g + 0]), __uint_as_float(a[8 * g + 1]));
+                        o.y = pack_bf16(__uint_as_float(a[8 * g + 2]), __uint_as_float(a[8 * g + 3]));
+                        o.z = pack_bf16(__uint_as_float(a[8 * g + 4]), __uint_as_float(a[8 * g + 5]));
+                        o.w = pack_bf16(__uint_as_float(a[8 * g + 6]), __uint_as_float(a[8 * g + 7]));
+                        *reinterpret_cast<uint4 *>(act_row + (q * 4 + g) * ACT_LBO) = o;
+                    }
+                    if (P.debug_layers >= 0 && l == run_layers - 1 && live) {
+                        float *dst = P.debug_act + ((size_t)board * 49 + cell) * F + q * 32;
+                        for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(a[i]);
+                    }
+                }
+                if (writes_res) tmem_wait_st();
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar(B_ACT + tile));
+            }
+            if (P.debug_layers < 0) {
+                // ---- heads ----
+                mbar_wait(bar(B_ACC + tile), acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                uint32_t a[32];
+                tmem_ld32(lane_addr + TM_ACC + tile * 128, a);
+                tmem_wait_ld();
+                float vterm = 0.f;
+                if (live) {
+                    float *dst = P.logits + (size_t)board * AZ_LOGITS + cell * 17;
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) dst[i] = __uint_as_float(a[i]);
+                    vterm = __uint_as_float(a[17]) * __ldg(P.fc_w + cell);
+                }
+                // value head: sum over the board's 49 cells (one board = 2 warps), then tanh
+#pragma unroll
+                for (int s = 16; s; s >>= 1) vterm += __shfl_xor_sync(0xffffffffu, vterm, s);
+                if (lane == 0) vpart[quad] = vterm;
+                tc_fence_before();
+                group_sync(tile);
+                if (gtid < 2) {
+                    const int b = unit * UNIT_BOARDS + tile * 2 + gtid;
+                    if (b < P.n) P.values[b] = tanhf(vpart[2 * gtid] + vpart[2 * gtid + 1] + __ldg(P.fc_b));
+                }
+                group_sync(tile);
+                // accumulator columns are free again for the next unit's input conv: the MMA warp waits on B_IN,
+                // which this thread arrives on only after the loads above completed.
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+
+static __nv_bfloat16 to_bf16(float v) { return __float2bfloat16_rn(v); }
+
+int az_net_tc_prepare(az_context *ctx, AzNet *net, const std::vector<float> &h)
+{
+    (void)ctx;
+    const int f = net->filters, blocks = net->blocks, layers = net->layers;
+    const size_t n_in = 9 * 4 * (size_t)f, n_tower = (size_t)2 * blocks * 9 * f * f;
+    const float *w_in = h.data();
+    const float *w_tower = w_in + n_in;
+    const float *w_policy = w_tower + n_tower;
+    const float *w_value = w_policy + (size_t)f * 17;
+    const float *bn = w_value + f + 49 + 1;
+    std::vector<float> scale((size_t)layers * f), shift((size_t)layers * f);
+    for (int l = 0; l < layers; ++l)
+        for (int c = 0; c < f; ++c) {
+            const double s = 1.0 / std::sqrt((double)bn[(size_t)(2 * l + 1) * f + c] + (double)AZ_BN_EPS);
+            scale[(size_t)l * f + c] = (float)s;
+            shift[(size_t)l * f + c] = (float)(-(double)bn[(size_t)(2 * l) * f + c] * s);
+        }
+    // tower: [layer][chunk = half*9 + tap][kg 0..7][cout][i 0..7]
+    std::vector<__nv_bfloat16> tw((size_t)2 * blocks * CHUNKS * 8 * f * 8);
+    for (int l = 0; l < 2 * blocks; ++l)
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int half = c / 9, tap = c % 9;
+            for (int kg = 0; kg < 8; ++kg)
+                for (int co = 0; co < f; ++co)
+                    for (int i = 0; i < 8; ++i) {
+                        const int cin = half * 64 + kg * 8 + i;
+                        const float w = w_tower[(((size_t)l * 9 + tap) * f + cin) * f + co] * scale[(size_t)(l + 1) * f + co];
+                        tw[((((size_t)l * CHUNKS + c) * 8 + kg) * f + co) * 8 + i] = to_bf16(w);
+                    }
+        }
+    // input conv: [kstep j][g][cout][i]: tap = 2j+g (tap 9 = zero), channels 0..3 real
+    std::vector<__nv_bfloat16> wi((size_t)5 * 2 * f * 8);
+    for (int j = 0; j < 5; ++j)
+        for (int g = 0; g < 2; ++g)
+            for (int co = 0; co < f; ++co)
+                for (int i = 0; i < 8; ++i) {
+                    const int tap = 2 * j + g;
+                    float w = 0.f;
+                    if (tap < 9 && i < 4) w = w_in[((size_t)tap * 4 + i) * f + co] * scale[co];
+                    wi[(((size_t)j * 2 + g) * f + co) * 8 + i] = to_bf16(w);
+                }
+    // heads: [kg][row 0..31][i]: rows 0..16 policy planes, row 17 value plane
+    std::vector<__nv_bfloat16> wh((size_t)KG * HEAD_N * 8);
+    for (int kg = 0; kg < KG; ++kg)
+        for (int row = 0; row < HEAD_N; ++row)
+            for (int i = 0; i < 8; ++i) {
+                const int cin = kg * 8 + i;
+                float w = 0.f;
+                if (row < 17) w = w_policy[(size_t)cin * 17 + row];
+                else if (row == 17) w = w_value[cin];
+                wh[((size_t)kg * HEAD_N + row) * 8 + i] = to_bf16(w);
+            }
+    AZ_CUDA(cudaMalloc(&net->tc_w, tw.size() * 2));
+    AZ_CUDA(cudaMemcpy(net->tc_w, tw.data(), tw.size() * 2, cudaMemcpyHostToDevice));
+    AZ_CUDA(cudaMalloc(&net->tc_w_in, wi.size() * 2));
+    AZ_CUDA(cudaMemcpy(net->tc_w_in, wi.data(), wi.size() * 2, cudaMemcpyHostToDevice));
+    AZ_CUDA(cudaMalloc(&net->tc_w_heads, wh.size() * 2));
+    AZ_CUDA(cudaMemcpy(net->tc_w_heads, wh.data(), wh.size() * 2, cudaMemcpyHostToDevice));
+    AZ_CUDA(cudaMalloc(&net->tc_shift, shift.size() * 4));
+    AZ_CUDA(cudaMemcpy(net->tc_shift, shift.data(), shift.size() * 4, cudaMemcpyHostToDevice));
+    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<AZ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<AZ_IN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    return AZ_OK;
+}
+
+void az_net_tc_release(AzNet *net)
+{
+    if (net->tc_w) cudaFree(net->tc_w);
+    if (net->tc_w_in) cudaFree(net->tc_w_in);
+    if (net->tc_w_heads) cudaFree(net->tc_w_heads);
+    if (net->tc_shift) cudaFree(net->tc_shift);
+    net->tc_w = net->tc_w_in = net->tc_w_heads = nullptr;
+    net->tc_shift = nullptr;
+}
+
+static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
+                     int debug_layers, float *d_debug)
+{
+    TcParams P;
+    P.input = d_in;
+    P.n = n;
+    P.layers = net->layers;
+    P.debug_layers = debug_layers;
+    P.w_tower = net->tc_w;
+    P.w_in = net->tc_w_in;
+    P.w_heads = net->tc_w_heads;
+    P.shift = net->tc_shift;
+    P.fc_w = net->fc_w;
+    P.fc_b = net->fc_b;
+    P.logits = d_logits;
+    P.values = d_values;
+    P.debug_act = d_debug;
+    const int units = (n + UNIT_BOARDS - 1) / UNIT_BOARDS;
+    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
+    if (in_kind == AZ_IN_F32)
+        k_net_tc<AZ_IN_F32><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(P);
+    else
+        k_net_tc<AZ_IN_POS><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(P);
+    ctx->launches++;
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values)
+{
+    return tc_launch(ctx, net, d_in, in_kind, n, d_logits, d_values, -1, nullptr);
+}
+
+// Debug/validation hook (not part of the public header): run the first `conv_layers` convolutions of the
+// tensor-core tower and return the fp32 (pre-bf16-rounding) activations [n][49][128] of the last one.
+extern "C" int az_net_debug_tower(az_context *ctx, const float *features, int n, int conv_layers, float *act_out)
+{
+    AZ_REQUIRE(ctx && ctx->net && features && act_out && n > 0, AZ_ERR_ARG, "az_net_debug_tower: bad argument");
+    AZ_REQUIRE(conv_layers >= 1 && conv_layers <= ctx->net->layers, AZ_ERR_ARG, "conv_layers out of range");
+    const size_t fb = sizeof(float) * AZ_FEATURES * (size_t)n, ab = sizeof(float) * 49 * F * (size_t)n;
+    AZ_REQUIRE(ctx->scratch[0].reserve(fb) == 0 && ctx->scratch[1].reserve(ab) == 0, AZ_ERR_CUDA, "scratch alloc");
+    AZ_CUDA(cudaMemcpyAsync(ctx->scratch[0].ptr, features, fb, cudaMemcpyHostToDevice, ctx->stream));
+    AZ_CUDA(cudaMemsetAsync(ctx->scratch[1].ptr, 0, ab, ctx->stream));
+    int rc = tc_launch(ctx, ctx->net, ctx->scratch[0].ptr, AZ_IN_F32, n, nullptr, nullptr, conv_layers, ctx->scratch[1].as<float>());
+    if (rc) return rc;
+    AZ_CUDA(cudaMemcpyAsync(act_out, ctx->scratch[1].ptr, ab, cudaMemcpyDeviceToHost, ctx->stream));
+    AZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}

@@ -92,6 +92,30 @@ int az_perft_batch_dev(az_context *ctx, const void *d_pos, int n, int depth, voi
 /* statistics of the last perft call: device-side counted parents ("count nodes") and kernel launches */
 int az_perft_last_stats(az_context *ctx, uint64_t *count_nodes, int32_t *launches, int32_t *frontier_items);
 
+/* ---------------- network (model.py:38-79 forward; .npy weights model.py:179-196) ------------- */
+/* Precision modes of the forward pass. */
+#define AZ_NET_FP32   0   /* CUDA-core fp32, reference-accurate (<= 1e-5 vs the fp32/fp64 restatement) */
+#define AZ_NET_BF16   1   /* bf16 tcgen05 tensor-core implicit GEMM, fp32 accumulate (<= 2e-2 abs)      */
+
+/* Upload weights.  `packed` is float32, host memory, in model.py parameter order:
+ *   W_in[3][3][4][F], then 2*blocks x W[3][3][F][F]   (TF layout [kh(x)][kw(y)][Cin][Cout]),
+ *   W_policy[F][17], W_value[F][1], fc_w[49], fc_b[1],
+ *   then for each of the 1+2*blocks batch-norm layers: moving_mean[F], moving_variance[F].
+ * Batch-norm is applied in inference form with gamma=1, beta=0, eps=1e-3 (model.py:120-124; gamma/beta
+ * are never stored in the .npy).  F must be 128 in this build. */
+int az_net_load(az_context *ctx, const float *packed, size_t count, int filters, int blocks);
+size_t az_net_param_count(int filters, int blocks);   /* expected `count` */
+
+/* sess.run([policy_output, value_output], {input_ph: features}) of accelerated_generate_games.py:57-63 /
+ * engine.py:184-190: features float32 [n][7][7][4] -> logits float32 [n][7][7][17], values float32 [n]. */
+int az_net_forward(az_context *ctx, const float *features, int n, int mode, float *logits, float *values);
+/* gpu_server.py:52-56 wire form: int8 features [n][196] (rpc_client.py:16-19) */
+int az_net_forward_i8(az_context *ctx, const int8_t *features, int n, int mode, float *logits, float *values);
+/* device-resident: d_features float32 [n][196]; d_logits [n][833]; d_values [n]; context stream, no sync */
+int az_net_forward_dev(az_context *ctx, const void *d_features, int n, int mode, void *d_logits, void *d_values);
+/* fused leaf encoding (self_play_client.cpp:174-202) + forward: d_pos is az_position[n] on the device */
+int az_net_forward_pos_dev(az_context *ctx, const void *d_pos, int n, int mode, void *d_logits, void *d_values);
+
 #ifdef __cplusplus
 }
 #endif
