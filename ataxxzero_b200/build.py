@@ -56,7 +56,9 @@ def build(force=False, verbose=False):
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
             continue
-        cmd = [nvcc()] + host_compiler_args() + ARCH + NVCC_FLAGS + ["-c", src, "-o", obj]
+        first = open(src).readline()
+        extra = first.split("AZ_NVCC_FLAGS:", 1)[1].split() if "AZ_NVCC_FLAGS:" in first else []
+        cmd = [nvcc()] + host_compiler_args() + ARCH + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd))
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -86,8 +86,11 @@ __device__ __forceinline__ void conv3x3(const float *__restrict__ in, float *__r
 
 template <int IN_KIND>
 __global__ void __launch_bounds__(THREADS, 1)
-k_net_fp32(const void *__restrict__ input, int n, AzNet net, float *__restrict__ logits, float *__restrict__ values)
+k_net_fp32(const void *__restrict__ input, int n_max, const int *__restrict__ n_ptr, AzNet net, float *__restrict__ logits,
+           float *__restrict__ values)
 {
+    const int n = n_ptr ? min(*n_ptr, n_max) : n_max;
+    if (blockIdx.x * NB >= n) return;
     extern __shared__ __align__(16) float smem[];
     float *bufX = smem;
     float *bufY = smem + ROWS * F;
@@ -222,7 +225,8 @@ extern "C" int az_net_load(az_context *ctx, const float *packed, size_t count, i
     return AZ_OK;
 }
 
-static int net_forward_dev(az_context *ctx, const void *d_in, int in_kind, int n, int mode, void *d_logits, void *d_values)
+static int net_forward_dev(az_context *ctx, const void *d_in, int in_kind, int n, int mode, void *d_logits, void *d_values,
+                           const int *d_count = nullptr)
 {
     AZ_REQUIRE(ctx && (n == 0 || (d_in && d_logits && d_values)), AZ_ERR_ARG, "az_net_forward: null argument");
     AZ_REQUIRE(ctx->net, AZ_ERR_STATE, "az_net_forward: no weights loaded (call az_net_load first)");
@@ -230,17 +234,23 @@ static int net_forward_dev(az_context *ctx, const void *d_in, int in_kind, int n
     AZ_REQUIRE(mode == AZ_NET_FP32 || mode == AZ_NET_BF16, AZ_ERR_ARG, "az_net_forward: unknown mode %d", mode);
     if (n == 0) return AZ_OK;
     if (mode == AZ_NET_BF16)
-        return az_net_tc_forward(ctx, ctx->net, d_in, in_kind, n, static_cast<float *>(d_logits), static_cast<float *>(d_values));
+        return az_net_tc_forward(ctx, ctx->net, d_in, in_kind, n, static_cast<float *>(d_logits), static_cast<float *>(d_values), d_count);
     const int grid = (n + NB - 1) / NB;
     if (in_kind == AZ_IN_F32)
-        k_net_fp32<AZ_IN_F32><<<grid, THREADS, SMEM_FP32, ctx->stream>>>(d_in, n, *ctx->net, static_cast<float *>(d_logits),
+        k_net_fp32<AZ_IN_F32><<<grid, THREADS, SMEM_FP32, ctx->stream>>>(d_in, n, d_count, *ctx->net, static_cast<float *>(d_logits),
                                                                        static_cast<float *>(d_values));
     else
-        k_net_fp32<AZ_IN_POS><<<grid, THREADS, SMEM_FP32, ctx->stream>>>(d_in, n, *ctx->net, static_cast<float *>(d_logits),
+        k_net_fp32<AZ_IN_POS><<<grid, THREADS, SMEM_FP32, ctx->stream>>>(d_in, n, d_count, *ctx->net, static_cast<float *>(d_logits),
                                                                        static_cast<float *>(d_values));
     ctx->launches++;
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
+}
+
+int az_net_forward_internal(az_context *ctx, const void *d_in, int in_kind, int n, int mode, float *d_logits, float *d_values,
+                            const int *d_count)
+{
+    return net_forward_dev(ctx, d_in, in_kind, n, mode, d_logits, d_values, d_count);
 }
 
 extern "C" int az_net_forward_dev(az_context *ctx, const void *d_features, int n, int mode, void *d_logits, void *d_values)

@@ -26,7 +26,11 @@ struct AzNet {
 
 // az_net_tc.cu
 int az_net_tc_prepare(az_context *ctx, AzNet *net, const std::vector<float> &host_packed);
-int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values);
+int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
+                      const int *d_count = nullptr);
+// internal: forward over up to `n` boards; when d_count != nullptr the actual count is read on the device
+int az_net_forward_internal(az_context *ctx, const void *d_in, int in_kind, int n, int mode, float *d_logits, float *d_values,
+                            const int *d_count);
 void az_net_tc_release(AzNet *net);
 
 enum { AZ_IN_F32 = 0, AZ_IN_POS = 1 };

@@ -187,6 +187,7 @@ __device__ __forceinline__ void group_sync(int tile) { asm volatile("bar.sync %0
 struct TcParams {
     const void *input;                 // float[n][196] or az_position[n]
     int n;                             // boards
+    const int *n_ptr;                  // when non-null the board count is read from device memory
     int layers;                        // 1 + 2*blocks
     int debug_layers;                  // >= 0: stop after this many conv layers and dump activations
     const __nv_bfloat16 *w_tower;      // [2*blocks][18][8][128][8]
@@ -221,7 +222,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
     const int B_FULL = 0, B_EMPTY = STAGES, B_ACC = 2 * STAGES, B_ACT = 2 * STAGES + TILES, B_CONST = 2 * STAGES + 2 * TILES;
     const int B_IN = B_CONST + 1;      // input planes staged (arrived by the epilogue threads)
 
-    const int num_units = (P.n + UNIT_BOARDS - 1) / UNIT_BOARDS;
+    const int n_boards = P.n_ptr ? min(*P.n_ptr, P.n) : P.n;
+    const int num_units = (n_boards + UNIT_BOARDS - 1) / UNIT_BOARDS;
     const int tower_layers = P.layers - 1;          // tensor-core 128->128 convs
     const int run_layers = P.debug_layers >= 0 ? min(P.debug_layers, P.layers) : P.layers;   // conv layers executed (incl. input conv)
 
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
 
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
             const int board = unit * UNIT_BOARDS + tile * 2 + bit;
-            const bool live = real && board < P.n;
+            const bool live = real && board < n_boards;
             // ---- stage the input planes of this row: 4 feature channels + 4 zeros, bf16 ----
             {
                 uint4 v = make_uint4(0, 0, 0, 0);
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
                 group_sync(tile);
                 if (gtid < 2) {
                     const int b = unit * UNIT_BOARDS + tile * 2 + gtid;
-                    if (b < P.n) P.values[b] = tanhf(vpart[2 * gtid] + vpart[2 * gtid + 1] + __ldg(P.fc_b));
+                    if (b < n_boards) P.values[b] = tanhf(vpart[2 * gtid] + vpart[2 * gtid + 1] + __ldg(P.fc_b));
                 }
                 group_sync(tile);
                 // accumulator columns are free again for the next unit's input conv: the MMA warp waits on B_IN,
@@ -537,11 +539,12 @@ void az_net_tc_release(AzNet *net)
 }
 
 static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
-                     int debug_layers, float *d_debug)
+                     int debug_layers, float *d_debug, const int *d_count = nullptr)
 {
     TcParams P;
     P.input = d_in;
     P.n = n;
+    P.n_ptr = d_count;
     P.layers = net->layers;
     P.debug_layers = debug_layers;
     P.w_tower = net->tc_w;
@@ -564,9 +567,10 @@ static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind,
     return AZ_OK;
 }
 
-int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values)
+int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
+                      const int *d_count)
 {
-    return tc_launch(ctx, net, d_in, in_kind, n, d_logits, d_values, -1, nullptr);
+    return tc_launch(ctx, net, d_in, in_kind, n, d_logits, d_values, -1, nullptr, d_count);
 }
 
 // Debug/validation hook (not part of the public header): run the first `conv_layers` convolutions of the

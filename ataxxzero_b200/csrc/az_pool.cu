@@ -1,0 +1,576 @@
+// az_pool.cu -- host runtime of the device-resident game pool: allocation, the tick loop
+// (tree kernel <-> net kernel, no host round trip per evaluation), external-evaluator stepping,
+// reference-format JSON game records, and the legacy 4-function ABI of link.py.
+//
+// Replaces the thread pool / double-buffered request queue of cpp/self_play_client.cpp:588-749 and
+// the Python feed loop of accelerated_generate_games.py:54-83.
+#include "az_net.h"
+#include "az_tree.cuh"
+
+#include <algorithm>
+#include <charconv>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+using namespace aztree;
+
+void aztree_launch_tick(const PoolDev &P, cudaStream_t s);
+void aztree_launch_init_all(const PoolDev &P, const az_position &pos, cudaStream_t s);
+void aztree_launch_set_root(const PoolDev &P, int g, const az_position &pos, cudaStream_t s);
+void aztree_launch_play(const PoolDev &P, int g, int move, int *d_status, cudaStream_t s);
+void aztree_launch_release(const PoolDev &P, const DoneEntry *d_done, int n, cudaStream_t s);
+void aztree_launch_features(const az_position *d_pos, int n, float *d_out, cudaStream_t s);
+
+struct az_pool {
+    az_context *ctx = nullptr;
+    az_pool_config cfg{};
+    PoolDev dev{};
+    size_t node_bytes = 0;
+    int32_t *d_status = nullptr;
+    float *d_features = nullptr;          // external mode: [G][196]
+    DoneEntry *d_done_snapshot = nullptr; // copy of the done queue being drained
+    // pinned host mirrors
+    int32_t *h_counts = nullptr;          // [0] req_count, [1] done_count, [2] status
+    DoneEntry *h_done = nullptr;          // [2G]
+    uint32_t *h_record = nullptr;         // one record buffer
+    std::vector<Game> h_games;
+    int pending_requests = 0;             // external mode: requests handed out by collect()
+    uint64_t ticks = 0, launches = 0;
+    double net_seconds = 0.0, tree_seconds = 0.0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    uint64_t written_games = 0, written_positions = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(T **p, size_t count, bool zero = true)
+{
+    AZ_CUDA(cudaMalloc(p, sizeof(T) * count));
+    if (zero) AZ_CUDA(cudaMemset(*p, 0, sizeof(T) * count));
+    return AZ_OK;
+}
+
+const char *kErrNames[] = {"", "node pool exhausted", "selection path longer than 1024 plies", ">= 256 legal moves"};
+
+int check_game_errors(az_pool *pool)
+{
+    // called after a sync: any game in ST_ERROR turns into AZ_ERR_CAPACITY
+    AZ_CUDA(cudaMemcpy(pool->h_games.data(), pool->dev.games, sizeof(Game) * pool->dev.G, cudaMemcpyDeviceToHost));
+    for (int g = 0; g < pool->dev.G; ++g)
+        if (pool->h_games[g].status == ST_ERROR)
+            return az_fail(AZ_ERR_CAPACITY, "game %d: %s", g, kErrNames[std::min(std::max(pool->h_games[g].error, 0), 3)]);
+    return AZ_OK;
+}
+
+// ---- one tick: (previous evaluations ->) tree kernel -> requests ----
+int launch_tree(az_pool *pool, bool consume = true)
+{
+    cudaStream_t s = pool->ctx->stream;
+    if (consume) AZ_CUDA(cudaMemsetAsync(pool->dev.req_count, 0, sizeof(int32_t), s));
+    pool->dev.consume = consume ? 1 : 0;
+    aztree_launch_tick(pool->dev, s);
+    pool->ticks++;
+    pool->launches++;
+    pool->ctx->launches++;
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+int launch_net(az_pool *pool)
+{
+    int rc = az_net_forward_internal(pool->ctx, pool->dev.req_pos, AZ_IN_POS, pool->dev.G, pool->cfg.eval_mode, pool->dev.logits,
+                                     pool->dev.values, pool->dev.req_count);
+    pool->launches++;
+    return rc;
+}
+
+// ---- JSON (nlohmann::json::dump() conventions: no spaces, keys sorted, shortest round-trip doubles) ----
+void append_double(std::string &out, double v)
+{
+    char buf[40];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v);
+    std::string s(buf, r.ptr);
+    if (s.find_first_of(".en") == std::string::npos) s += ".0";     // 1 -> 1.0, like nlohmann
+    out += s;
+}
+
+std::string record_to_json(const uint32_t *rec, int words, int plies, int result)
+{
+    std::string boards = "[", dists = "[", moves = "[";
+    int w = 0;
+    char mvbuf[8];
+    for (int p = 0; p < plies && w < words; ++p) {
+        const uint64_t x = (uint64_t)rec[w] | ((uint64_t)rec[w + 1] << 32), o = (uint64_t)rec[w + 2] | ((uint64_t)rec[w + 3] << 32);
+        const az_move mv = (az_move)(rec[w + 4] & 0xffff);
+        const int entries = (int)(rec[w + 4] >> 16);
+        const double total = (double)rec[w + 5];
+        if (p) { boards += ","; dists += ","; moves += ","; }
+        boards += "[";
+        for (int y = 0; y < 7; ++y)                                  // serialize_board_for_json (:88-107): top row first
+            for (int xx = 0; xx < 7; ++xx) {
+                const uint64_t bit = 1ULL << (xx + 7 * (6 - y));
+                if (y || xx) boards += ",";
+                boards += (x & bit) ? "1" : (o & bit) ? "2" : "0";
+            }
+        boards += "]";
+        az_move_string(mv, mvbuf);
+        moves += "\"";
+        moves += mvbuf;
+        moves += "\"";
+        std::map<std::string, double> dist;                           // nlohmann objects are std::map: keys sorted
+        for (int e = 0; e < entries; ++e) {
+            az_move_string((az_move)(rec[w + 6 + 2 * e] & 0xffff), mvbuf);
+            dist[mvbuf] = (double)rec[w + 7 + 2 * e] / total;
+        }
+        dists += "{";
+        bool first = true;
+        for (auto &kv : dist) {
+            if (!first) dists += ",";
+            first = false;
+            dists += "\"" + kv.first + "\":";
+            append_double(dists, kv.second);
+        }
+        dists += "}";
+        w += 6 + 2 * entries;
+    }
+    return "{\"boards\":" + boards + "],\"dists\":" + dists + "],\"moves\":" + moves + "],\"result\":" + std::to_string(result) + "}";
+}
+
+// copy out finished games, append them to `out` (may be null: records are dropped), release the buffers
+int drain_finished(az_pool *pool, FILE *out, int64_t *games_written)
+{
+    cudaStream_t s = pool->ctx->stream;
+    AZ_CUDA(cudaMemcpyAsync(pool->h_counts + 1, pool->dev.done_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    const int n = pool->h_counts[1];
+    if (n == 0) return AZ_OK;
+    AZ_CUDA(cudaMemcpyAsync(pool->h_done, pool->dev.done, sizeof(DoneEntry) * n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(pool->d_done_snapshot, pool->dev.done, sizeof(DoneEntry) * n, cudaMemcpyDeviceToDevice, s));
+    AZ_CUDA(cudaMemsetAsync(pool->dev.done_count, 0, sizeof(int32_t), s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) {
+        const DoneEntry &d = pool->h_done[i];
+        const uint32_t *src = pool->dev.records + ((size_t)d.game * 2 + d.buf) * pool->dev.rec_cap_words;
+        AZ_CUDA(cudaMemcpyAsync(pool->h_record, src, sizeof(uint32_t) * d.words, cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaStreamSynchronize(s));
+        if (out) {
+            const std::string line = record_to_json(pool->h_record, d.words, d.plies, d.result);
+            if (fwrite(line.data(), 1, line.size(), out) != line.size() || fputc('\n', out) == EOF)
+                return az_fail(AZ_ERR_IO, "short write to the game file");
+            fflush(out);                                              // one flushed line per game (:641-642)
+        }
+        pool->written_games++;
+        pool->written_positions += d.plies;
+        if (games_written) (*games_written)++;
+    }
+    aztree_launch_release(pool->dev, pool->d_done_snapshot, n, s);
+    pool->launches++;
+    return AZ_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_pool **out)
+{
+    AZ_REQUIRE(ctx && cfg && out, AZ_ERR_ARG, "az_pool_create: null argument");
+    *out = nullptr;
+    AZ_REQUIRE(cfg->games >= 1 && cfg->games <= (1 << 20), AZ_ERR_ARG, "az_pool_create: games=%d", cfg->games);
+    AZ_REQUIRE(cfg->visits >= 1 && cfg->visits <= (1 << 22), AZ_ERR_ARG, "az_pool_create: visits=%d", cfg->visits);
+    AZ_REQUIRE(cfg->eval_mode == AZ_NET_FP32 || cfg->eval_mode == AZ_NET_BF16 || cfg->eval_mode == AZ_EVAL_EXTERNAL, AZ_ERR_ARG,
+               "az_pool_create: eval_mode=%d", cfg->eval_mode);
+    AZ_REQUIRE(cfg->eval_mode == AZ_EVAL_EXTERNAL || ctx->net, AZ_ERR_STATE, "az_pool_create: no weights loaded (az_net_load)");
+    az_position start;
+    const char *fen = cfg->start_fen[0] ? cfg->start_fen : "startpos";
+    AZ_REQUIRE(az_set_board(&start, fen) == 0, AZ_ERR_ARG, "az_pool_create: bad start_fen '%s'", fen);
+
+    az_pool *pool = new az_pool();
+    pool->ctx = ctx;
+    pool->cfg = *cfg;
+    if (pool->cfg.max_plies <= 0) pool->cfg.max_plies = 400;
+    if (pool->cfg.node_capacity <= 0) pool->cfg.node_capacity = cfg->visits + 64;
+    if (pool->cfg.steps_per_tick <= 0) pool->cfg.steps_per_tick = 16;
+    AZ_REQUIRE(pool->cfg.node_capacity < (1 << 24), AZ_ERR_ARG, "az_pool_create: node_capacity too large");
+    PoolDev &D = pool->dev;
+    D.G = cfg->games;
+    D.C = pool->cfg.node_capacity;
+    D.visits = cfg->visits;
+    D.max_plies = pool->cfg.max_plies;
+    D.noise = cfg->noise ? 1 : 0;
+    D.auto_play = cfg->auto_play ? 1 : 0;
+    D.steps_per_tick = pool->cfg.steps_per_tick;
+    D.seed = cfg->seed;
+    D.rec_cap_words = cfg->auto_play ? (uint32_t)pool->cfg.max_plies * kRecWordsPerPly : 16;
+    const size_t G = (size_t)D.G;
+    pool->node_bytes = G * D.C * kNodeStride;
+    size_t free_b = 0, total_b = 0;
+    AZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = pool->node_bytes + G * 2 * D.rec_cap_words * 4 + G * (kMaxPath + D.C) * 4 + G * 4096;
+    if (need > free_b) {
+        delete pool;
+        return az_fail(AZ_ERR_CAPACITY, "az_pool_create: needs %.1f GiB of HBM, %.1f GiB free", need / 1073741824.0, free_b / 1073741824.0);
+    }
+    int rc = 0;
+    rc |= dev_alloc(&D.nodes, pool->node_bytes, false);
+    rc |= dev_alloc(&D.games, G);
+    rc |= dev_alloc(&D.path, G * kMaxPath, false);
+    rc |= dev_alloc(&D.gstack, G * D.C, false);
+    rc |= dev_alloc(&D.req_pos, G);
+    rc |= dev_alloc(&D.req_game, G);
+    rc |= dev_alloc(&D.req_count, 1);
+    rc |= dev_alloc(&D.logits, G * AZ_LOGITS);
+    rc |= dev_alloc(&D.values, G);
+    rc |= dev_alloc(&D.records, G * 2 * D.rec_cap_words, false);
+    rc |= dev_alloc(&D.done, 2 * G);
+    rc |= dev_alloc(&D.done_count, 1);
+    rc |= dev_alloc(&pool->d_done_snapshot, 2 * G);
+    rc |= dev_alloc(&pool->d_status, 4);
+    rc |= dev_alloc(&pool->d_features, G * AZ_FEATURES);
+    if (rc) { az_pool_destroy(pool); return AZ_ERR_CUDA; }
+    AZ_CUDA(cudaMallocHost(&pool->h_counts, 16 * sizeof(int32_t)));
+    AZ_CUDA(cudaMallocHost(&pool->h_done, sizeof(DoneEntry) * 2 * G));
+    AZ_CUDA(cudaMallocHost(&pool->h_record, sizeof(uint32_t) * D.rec_cap_words));
+    pool->h_games.resize(G);
+    for (auto &e : pool->ev) AZ_CUDA(cudaEventCreate(&e));
+    aztree_launch_init_all(D, start, ctx->stream);
+    pool->launches++;
+    AZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    AZ_CUDA(cudaGetLastError());
+    if ((rc = check_game_errors(pool))) { az_pool_destroy(pool); return rc; }
+    *out = pool;
+    return AZ_OK;
+}
+
+extern "C" void az_pool_destroy(az_pool *pool)
+{
+    if (!pool) return;
+    cudaStreamSynchronize(pool->ctx->stream);
+    PoolDev &D = pool->dev;
+    void *ptrs[] = {D.nodes, D.games, D.path, D.gstack, D.req_pos, D.req_game, D.req_count, D.logits, D.values, D.records,
+                    D.done, D.done_count, pool->d_done_snapshot, pool->d_status, pool->d_features};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (pool->h_counts) cudaFreeHost(pool->h_counts);
+    if (pool->h_done) cudaFreeHost(pool->h_done);
+    if (pool->h_record) cudaFreeHost(pool->h_record);
+    for (auto &e : pool->ev)
+        if (e) cudaEventDestroy(e);
+    delete pool;
+}
+
+extern "C" int az_pool_stats_get(az_pool *pool, az_pool_stats *out)
+{
+    AZ_REQUIRE(pool && out, AZ_ERR_ARG, "az_pool_stats_get: null argument");
+    AZ_CUDA(cudaStreamSynchronize(pool->ctx->stream));
+    AZ_CUDA(cudaMemcpy(pool->h_games.data(), pool->dev.games, sizeof(Game) * pool->dev.G, cudaMemcpyDeviceToHost));
+    az_pool_stats s{};
+    for (const Game &g : pool->h_games) {
+        s.steps += g.steps;
+        s.evals += g.evals;
+        s.terminal_steps += g.terminal_steps;
+        s.positions += g.positions;
+        s.games_finished += g.finished;
+        s.games_skipped += g.skipped;
+        s.max_depth = std::max<uint64_t>(s.max_depth, g.max_depth);
+    }
+    s.ticks = pool->ticks;
+    s.kernel_launches = pool->launches;
+    s.net_seconds = pool->net_seconds;
+    s.tree_seconds = pool->tree_seconds;
+    *out = s;
+    return AZ_OK;
+}
+
+extern "C" int az_pool_set_root(az_pool *pool, int game, const az_position *root)
+{
+    AZ_REQUIRE(pool && root, AZ_ERR_ARG, "az_pool_set_root: null argument");
+    AZ_REQUIRE(game >= 0 && game < pool->dev.G, AZ_ERR_ARG, "az_pool_set_root: game %d out of range", game);
+    AZ_REQUIRE(pool->pending_requests == 0, AZ_ERR_STATE, "az_pool_set_root: evaluations are outstanding (az_pool_provide first)");
+    const uint64_t all = root->pieces[0] | root->pieces[1] | root->blockers;
+    AZ_REQUIRE(!(root->pieces[0] & root->pieces[1]) && !((root->pieces[0] | root->pieces[1]) & root->blockers) &&
+                   !(all >> 49) && (root->pieces[0] | root->pieces[1]),
+               AZ_ERR_ARG, "az_pool_set_root: invalid position");
+    aztree_launch_set_root(pool->dev, game, *root, pool->ctx->stream);
+    pool->launches++;
+    AZ_CUDA(cudaStreamSynchronize(pool->ctx->stream));
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+extern "C" int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out)
+{
+    AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_run: null pool");
+    AZ_REQUIRE(pool->cfg.eval_mode != AZ_EVAL_EXTERNAL, AZ_ERR_STATE, "az_pool_run: pool uses an external evaluator (collect/provide)");
+    cudaStream_t s = pool->ctx->stream;
+    if (idle_out) *idle_out = 0;
+    for (int t = 0; t < max_ticks; ++t) {
+        int rc = launch_tree(pool);
+        if (rc) return rc;
+        AZ_CUDA(cudaMemcpyAsync(pool->h_counts, pool->dev.req_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if ((rc = launch_net(pool))) return rc;
+        AZ_CUDA(cudaStreamSynchronize(s));
+        if (pool->h_counts[0] == 0) {           // nobody asked for an evaluation: every tree is done (or stalled)
+            if (idle_out) *idle_out = 1;
+            break;
+        }
+    }
+    AZ_CUDA(cudaGetLastError());
+    return check_game_errors(pool);
+}
+
+extern "C" int az_pool_collect(az_pool *pool, float *features, int32_t *n_requests)
+{
+    AZ_REQUIRE(pool && features && n_requests, AZ_ERR_ARG, "az_pool_collect: null argument");
+    AZ_REQUIRE(pool->cfg.eval_mode == AZ_EVAL_EXTERNAL, AZ_ERR_STATE, "az_pool_collect: pool uses the internal net");
+    AZ_REQUIRE(pool->pending_requests == 0, AZ_ERR_STATE, "az_pool_collect: previous requests not answered (az_pool_provide)");
+    cudaStream_t s = pool->ctx->stream;
+    *n_requests = 0;
+    // The first tick consumes the evaluations handed in by az_pool_provide.  A tree may burn its step budget
+    // on adjudicated leaves without reaching a leaf that needs the net, so "top-up" ticks (which leave the
+    // already-waiting games alone and append to the request list) run until no tree can make progress.
+    for (int attempt = 0; attempt < 65536; ++attempt) {
+        int rc = launch_tree(pool, attempt == 0);
+        if (rc) return rc;
+        AZ_CUDA(cudaMemcpyAsync(pool->h_counts, pool->dev.req_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaStreamSynchronize(s));
+        if ((rc = check_game_errors(pool))) return rc;
+        bool busy = false;
+        for (int g = 0; g < pool->dev.G; ++g) busy |= pool->h_games[g].status == ST_IDLE;
+        if (!busy) break;                       // every tree is waiting, done or stalled
+    }
+    const int n = pool->h_counts[0];
+    if (n > 0) {
+        aztree_launch_features(pool->dev.req_pos, n, pool->d_features, s);
+        pool->launches++;
+        AZ_CUDA(cudaMemcpyAsync(features, pool->d_features, sizeof(float) * AZ_FEATURES * n, cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaStreamSynchronize(s));
+    }
+    AZ_CUDA(cudaGetLastError());
+    pool->pending_requests = n;
+    *n_requests = n;
+    return AZ_OK;
+}
+
+extern "C" int az_pool_provide(az_pool *pool, const float *logits, const float *values)
+{
+    AZ_REQUIRE(pool && logits && values, AZ_ERR_ARG, "az_pool_provide: null argument");
+    AZ_REQUIRE(pool->pending_requests > 0, AZ_ERR_STATE, "az_pool_provide: no outstanding requests");
+    const int n = pool->pending_requests;
+    cudaStream_t s = pool->ctx->stream;
+    AZ_CUDA(cudaMemcpyAsync(pool->dev.logits, logits, sizeof(float) * AZ_LOGITS * n, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaMemcpyAsync(pool->dev.values, values, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaStreamSynchronize(s));      // the caller may free its arrays right away (complete_workload copies too)
+    pool->pending_requests = 0;
+    return AZ_OK;
+}
+
+extern "C" int az_pool_root(az_pool *pool, int game, az_position *pos, int32_t *n_moves, az_move *moves, int32_t *visits,
+                            double *total_score, double *prior, int32_t *root_visits, double *root_value)
+{
+    AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_root: null pool");
+    AZ_REQUIRE(game >= 0 && game < pool->dev.G, AZ_ERR_ARG, "az_pool_root: game %d out of range", game);
+    AZ_CUDA(cudaStreamSynchronize(pool->ctx->stream));
+    Game gm;
+    AZ_CUDA(cudaMemcpy(&gm, pool->dev.games + game, sizeof(Game), cudaMemcpyDeviceToHost));
+    AZ_REQUIRE(gm.status != ST_ERROR, AZ_ERR_CAPACITY, "game %d: %s", game, kErrNames[std::min(std::max(gm.error, 0), 3)]);
+    std::vector<uint8_t> slot(kNodeStride);
+    AZ_CUDA(cudaMemcpy(slot.data(), pool->dev.nodes + ((size_t)game * pool->dev.C + gm.root) * kNodeStride, kNodeStride,
+                       cudaMemcpyDeviceToHost));
+    const NodeHdr *h = reinterpret_cast<const NodeHdr *>(slot.data());
+    if (pos) {
+        pos->ply = gm.ply;
+        pos->turn = h->turn;
+        pos->blockers = gm.blockers;
+        pos->pieces[h->turn] = h->own;
+        pos->pieces[h->turn ^ 1] = h->opp;
+    }
+    if (n_moves) *n_moves = h->n_moves;
+    if (root_visits) *root_visits = h->N;
+    if (root_value) *root_value = h->value;
+    for (int i = 0; i < h->n_moves; ++i) {
+        if (moves) moves[i] = reinterpret_cast<const uint16_t *>(slot.data() + kOffMove)[i];
+        if (visits) visits[i] = (int32_t)reinterpret_cast<const uint32_t *>(slot.data() + kOffN)[i];
+        if (total_score) total_score[i] = reinterpret_cast<const double *>(slot.data() + kOffW)[i];
+        if (prior) prior[i] = reinterpret_cast<const double *>(slot.data() + kOffP)[i];
+    }
+    return AZ_OK;
+}
+
+extern "C" int az_pool_play(az_pool *pool, int game, az_move move)
+{
+    AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_play: null pool");
+    AZ_REQUIRE(game >= 0 && game < pool->dev.G, AZ_ERR_ARG, "az_pool_play: game %d out of range", game);
+    AZ_REQUIRE(pool->pending_requests == 0, AZ_ERR_STATE, "az_pool_play: evaluations are outstanding");
+    cudaStream_t s = pool->ctx->stream;
+    aztree_launch_play(pool->dev, game, (int)move, pool->d_status, s);
+    pool->launches++;
+    AZ_CUDA(cudaMemcpyAsync(pool->h_counts + 2, pool->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    AZ_CUDA(cudaGetLastError());
+    const int st = pool->h_counts[2];
+    AZ_REQUIRE(st != -1, AZ_ERR_ARG, "az_pool_play: move is not legal at the root of game %d", game);
+    AZ_REQUIRE(st != -2, AZ_ERR_STATE, "az_pool_play: game %d is waiting for an evaluation", game);
+    AZ_REQUIRE(st == 0, AZ_ERR_CAPACITY, "az_pool_play: node pool exhausted");
+    return AZ_OK;
+}
+
+extern "C" int az_selfplay_run(az_pool *pool, const char *output_path, int64_t target_games, int64_t target_positions,
+                               double max_seconds, az_pool_stats *stats_out)
+{
+    AZ_REQUIRE(pool, AZ_ERR_ARG, "az_selfplay_run: null pool");
+    AZ_REQUIRE(pool->cfg.auto_play, AZ_ERR_STATE, "az_selfplay_run: pool was created with auto_play = 0");
+    AZ_REQUIRE(pool->cfg.eval_mode != AZ_EVAL_EXTERNAL, AZ_ERR_STATE, "az_selfplay_run: external evaluator pools are driven by collect/provide");
+    AZ_REQUIRE(target_games > 0 || target_positions > 0 || max_seconds > 0, AZ_ERR_ARG, "az_selfplay_run: no stop condition");
+    FILE *out = nullptr;
+    if (output_path && output_path[0]) {
+        out = fopen(output_path, "a");            // append mode, like std::ios_base::app (:691)
+        if (!out) return az_fail(AZ_ERR_IO, "az_selfplay_run: cannot open '%s' for appending", output_path);
+    }
+    cudaStream_t s = pool->ctx->stream;
+    const auto t0 = std::chrono::steady_clock::now();
+    const uint64_t pos0 = pool->written_positions;
+    int64_t games = 0;
+    int rc = AZ_OK;
+    const int kTicksPerDrain = 32;
+    for (;;) {
+        for (int t = 0; t < kTicksPerDrain && rc == AZ_OK; ++t) {
+            const bool timed = (t == 0);        // sample device time of one tick per drain interval
+            if (timed) cudaEventRecord(pool->ev[0], s);
+            rc = launch_tree(pool);
+            if (timed) cudaEventRecord(pool->ev[1], s);
+            if (rc == AZ_OK) rc = launch_net(pool);
+            if (timed) cudaEventRecord(pool->ev[2], s);
+        }
+        if (rc) break;
+        if ((rc = drain_finished(pool, out, &games))) break;
+        float ms_tree = 0.f, ms_net = 0.f;
+        if (cudaEventElapsedTime(&ms_tree, pool->ev[0], pool->ev[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms_net, pool->ev[1], pool->ev[2]) == cudaSuccess) {
+            pool->tree_seconds += ms_tree * 1e-3 * kTicksPerDrain;      // extrapolated from the sampled tick
+            pool->net_seconds += ms_net * 1e-3 * kTicksPerDrain;
+        }
+        const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (target_games > 0 && games >= target_games) break;
+        if (target_positions > 0 && (int64_t)(pool->written_positions - pos0) >= target_positions) break;
+        if (max_seconds > 0 && elapsed >= max_seconds) break;
+        if ((pool->ticks & 1023) < (uint64_t)kTicksPerDrain && (rc = check_game_errors(pool))) break;
+    }
+    if (out) fclose(out);
+    if (rc) return rc;
+    if ((rc = check_game_errors(pool))) return rc;
+    if (stats_out) return az_pool_stats_get(pool, stats_out);
+    return AZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// legacy ABI (link.py:8-32).  Process-global like the reference (self_play_client.cpp:591-602).
+// Two halves of the pool play the role of the two fill buffers: get_workload() alternates between
+// them, so while the caller evaluates buffer i the other half's answers can already be applied.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Legacy {
+    az_context *ctx = nullptr;
+    az_pool *half[2] = {nullptr, nullptr};
+    float *fill[2] = {nullptr, nullptr};
+    int entries = 0;
+    int next = 0;
+    FILE *out = nullptr;
+    bool waiting[2] = {false, false};
+    std::vector<float> staging;
+} g_legacy;
+
+void legacy_die(const char *what)
+{
+    // the reference aborts on failed asserts / exceptions; so do we, loudly
+    fprintf(stderr, "libataxxzero legacy ABI: %s: %s\n", what, az_last_error());
+    abort();
+}
+}  // namespace
+
+extern "C" void launch_threads(char *output_path, int visits, float *fill_buffer1, float *fill_buffer2, int buffer_entries,
+                               int thread_count)
+{
+    if (g_legacy.ctx) legacy_die("launch_threads called twice without shutdown");
+    if (!fill_buffer1 || !fill_buffer2 || buffer_entries < 1 || thread_count != 2 * buffer_entries) {
+        az_fail(AZ_ERR_ARG, "need two fill buffers and thread_count == 2*buffer_entries (got %d, %d)", buffer_entries, thread_count);
+        legacy_die("launch_threads");
+    }
+    const char *dev_env = getenv("AZ_DEVICE");
+    if (az_create(dev_env ? atoi(dev_env) : 0, (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count(), &g_legacy.ctx))
+        legacy_die("az_create");
+    printf("Launching into %p, %p with %d entries and %d threads.\n", (void *)fill_buffer1, (void *)fill_buffer2, buffer_entries,
+           thread_count);
+    printf("Writing to: %s\n", output_path);
+    g_legacy.out = fopen(output_path, "a");
+    if (!g_legacy.out) { az_fail(AZ_ERR_IO, "cannot open '%s'", output_path); legacy_die("launch_threads"); }
+    g_legacy.fill[0] = fill_buffer1;
+    g_legacy.fill[1] = fill_buffer2;
+    g_legacy.entries = buffer_entries;
+    g_legacy.next = 0;
+    g_legacy.staging.resize((size_t)buffer_entries * AZ_FEATURES);
+    for (int h = 0; h < 2; ++h) {
+        az_pool_config cfg{};
+        cfg.games = buffer_entries;
+        cfg.visits = visits;
+        cfg.max_plies = 400;
+        cfg.noise = 1;
+        cfg.auto_play = 1;
+        cfg.eval_mode = AZ_EVAL_EXTERNAL;
+        cfg.steps_per_tick = 64;
+        cfg.seed = g_legacy.ctx->seed + 0x9E3779B97F4A7C15ULL * (h + 1);
+        if (az_pool_create(g_legacy.ctx, &cfg, &g_legacy.half[h])) legacy_die("az_pool_create");
+        g_legacy.waiting[h] = false;
+    }
+}
+
+extern "C" int get_workload(void)
+{
+    if (!g_legacy.ctx) { az_fail(AZ_ERR_STATE, "launch_threads not called"); legacy_die("get_workload"); }
+    const int h = g_legacy.next;
+    if (g_legacy.waiting[h]) { az_fail(AZ_ERR_STATE, "buffer %d was handed out and not completed", h); legacy_die("get_workload"); }
+    az_pool *pool = g_legacy.half[h];
+    // the reference hands out a buffer only when all `buffer_entries` slots are filled: every game of this
+    // half must be blocked on an evaluation.  Games that end are restarted inside the tick, so this terminates.
+    std::vector<float> &st = g_legacy.staging;
+    int32_t have = 0;
+    if (az_pool_collect(pool, st.data(), &have)) legacy_die("az_pool_collect");
+    if (have != g_legacy.entries) {
+        az_fail(AZ_ERR_STATE, "only %d of %d games requested an evaluation", have, g_legacy.entries);
+        legacy_die("get_workload");
+    }
+    std::memcpy(g_legacy.fill[h], st.data(), sizeof(float) * AZ_FEATURES * (size_t)have);
+    int64_t dummy = 0;
+    if (drain_finished(pool, g_legacy.out, &dummy)) legacy_die("drain");
+    g_legacy.waiting[h] = true;
+    g_legacy.next ^= 1;
+    return h;
+}
+
+extern "C" void complete_workload(int workload, float *posteriors, float *values)
+{
+    if (!g_legacy.ctx || workload < 0 || workload > 1 || !g_legacy.waiting[workload]) {
+        az_fail(AZ_ERR_STATE, "complete_workload(%d) without a matching get_workload", workload);
+        legacy_die("complete_workload");
+    }
+    if (az_pool_provide(g_legacy.half[workload], posteriors, values)) legacy_die("az_pool_provide");
+    g_legacy.waiting[workload] = false;
+}
+
+extern "C" void shutdown(void)
+{
+    if (!g_legacy.ctx) return;
+    for (int h = 0; h < 2; ++h) {
+        az_pool_destroy(g_legacy.half[h]);
+        g_legacy.half[h] = nullptr;
+        g_legacy.waiting[h] = false;
+    }
+    if (g_legacy.out) fclose(g_legacy.out);
+    g_legacy.out = nullptr;
+    az_destroy(g_legacy.ctx);
+    g_legacy.ctx = nullptr;                    // cleared so launch_threads may be called again (:744-748)
+}

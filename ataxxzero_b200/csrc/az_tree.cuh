@@ -1,0 +1,93 @@
+// az_tree.cuh -- device-resident PUCT trees: memory layout shared by az_tree.cu (kernels)
+// and az_pool.cu (host runtime).  Internal.
+//
+// One tree per game, one fixed-stride slot per node (no allocator metadata on the hot path):
+//
+//   node slot (7168 B, 128-B aligned):
+//     [   0,   64)  header: position, value, child count L, visit count N, flags
+//     [  64, 2112)  P[256]      f64  prior                      (self_play_client.cpp:151 posterior)
+//     [2112, 4160)  W[256]      f64  edge_total_score           (:283)
+//     [4160, 5184)  n[256]      u32  edge_visits                (:282; integral, so exact as u32)
+//     [5184, 6208)  child[256]  i32  child node index, -1 = no edge yet (:281)
+//     [6208, 6720)  move[256]   u16  from | to<<8, reference movegen order (cpp/movegen.cpp:16-66)
+//     [6720, 6976)  rank[256]   u8   position of the move in the reference's hash-map iteration order
+//                                    (select_action's `>=` tie-break walks that order, :345-358)
+//   Children of a node are a struct-of-arrays inside its slot, so a warp reads P/W/n of 32 children
+//   with three coalesced loads.  L < 256 is the reference's own bound (movegen.cpp:69).
+//
+// Dead subtrees are recycled lazily: re-rooting pushes the discarded siblings on a per-game stack;
+// allocating a node pops one entry and pushes that node's children.  The pool therefore never holds
+// more than (live nodes + 1) slots and is never compacted or copied.
+#pragma once
+#include "az_common.h"
+
+namespace aztree {
+
+constexpr int kNodeStride = 7168;
+constexpr int kOffP = 64, kOffW = 2112, kOffN = 4160, kOffChild = 5184, kOffMove = 6208, kOffRank = 6720;
+constexpr int kMaxPath = 1024;
+constexpr int kRecWordsPerPly = 6 + 2 * 256;    // worst-case record words per ply
+
+enum : uint32_t { NF_TERMINAL = 1u, NF_POPULATED = 2u };
+enum : int32_t { ST_IDLE = 0, ST_WAIT = 1, ST_DONE = 2, ST_STALL = 3, ST_ERROR = 4 };
+enum : int32_t { ERR_NODES = 1, ERR_PATH = 2, ERR_MOVES = 3 };
+
+struct __align__(16) NodeHdr {
+    uint64_t own, opp;       // pieces of the side to move / of the opponent
+    double value;            // evals.value: from the side to move's point of view
+    int32_t n_moves;         // L; 0 for adjudicated (terminal) nodes
+    int32_t N;               // all_edge_visits
+    int32_t turn;            // absolute side to move: 0 = x, 1 = o
+    uint32_t flags;
+    int32_t buckets;         // bucket count of the reference's posterior map after population
+    int32_t pad[5];
+};
+static_assert(sizeof(NodeHdr) == 64, "node header is 64 bytes");
+
+struct __align__(16) Game {
+    int32_t status;
+    int32_t root;
+    int32_t pending;         // node awaiting an evaluation (ST_WAIT)
+    int32_t path_len;
+    int32_t n_alloc;         // bump pointer of never-used node slots
+    int32_t gsp;             // garbage stack pointer
+    int32_t ply;
+    int32_t req_slot;
+    uint64_t blockers;
+    uint32_t rec_words;      // words written to the current record buffer
+    int32_t rec_buf;         // 0/1
+    int32_t rec_plies;
+    uint32_t games_started;  // RNG stream selector
+    int32_t rec_busy[2];     // record buffer handed to the host and not yet released
+    int32_t error;
+    int32_t start_turn;
+    uint64_t start_own, start_opp;    // starting position of this slot (side to move / opponent)
+    // statistics (summed by the host on demand)
+    unsigned long long steps, evals, terminal_steps, positions, finished, skipped, max_depth;
+    int32_t pad2[2];
+};
+
+struct DoneEntry {
+    int32_t game, buf, words, plies, result, pad[3];
+};
+
+struct PoolDev {
+    uint8_t *nodes;          // [G][C][kNodeStride]
+    Game *games;             // [G]
+    uint32_t *path;          // [G][kMaxPath]  node << 8 | slot
+    uint32_t *gstack;        // [G][C]
+    az_position *req_pos;    // [G]
+    int32_t *req_game;       // [G]
+    int32_t *req_count;      // [1]
+    float *logits;           // [G][833]
+    float *values;           // [G]
+    uint32_t *records;       // [G][2][rec_cap_words]
+    DoneEntry *done;         // [2G]
+    int32_t *done_count;     // [1]
+    int32_t G, C, visits, max_plies, noise, auto_play, steps_per_tick;
+    int32_t consume;         // 1: evaluations of the previous requests are in logits/values; 0: top-up tick, leave waiting games alone
+    uint32_t rec_cap_words;
+    uint64_t seed;
+};
+
+}  // namespace aztree

@@ -116,6 +116,77 @@ int az_net_forward_dev(az_context *ctx, const void *d_features, int n, int mode,
 /* fused leaf encoding (self_play_client.cpp:174-202) + forward: d_pos is az_position[n] on the device */
 int az_net_forward_pos_dev(az_context *ctx, const void *d_pos, int n, int mode, void *d_logits, void *d_values);
 
+/* ---------------- search / self-play over a pool of device-resident trees ------------------ */
+/* One pool = G concurrent games, one PUCT tree each, all state in HBM (replaces the 2*buffer_size
+ * std::threads + per-thread MCTS objects of self_play_client.cpp:369-493,608-646). */
+#define AZ_EVAL_EXTERNAL 2      /* evaluations are supplied by the caller (legacy contract / parity hook) */
+
+typedef struct az_pool az_pool;
+
+typedef struct {
+    int32_t games;          /* G: concurrent games (accelerated_generate_games.py: 2*buffer_size threads)      */
+    int32_t visits;         /* search until root.all_edge_visits >= visits (self_play_client.cpp:522)       */
+    int32_t max_plies;      /* maximum_game_plies = 400 (self_play_client.cpp:34)                            */
+    int32_t noise;          /* 1: Dirichlet(0.15) x 0.25 at every root (self_play_client.cpp:250-271)        */
+    int32_t auto_play;      /* 1: self-play (sample move ~ visits, record, re-root, restart finished games);
+                               0: search only (MCTS::step / MCTS::play driven by the caller)                 */
+    int32_t eval_mode;      /* AZ_NET_FP32, AZ_NET_BF16 or AZ_EVAL_EXTERNAL                                   */
+    int32_t node_capacity;  /* nodes per tree; 0 = visits + 64                                               */
+    int32_t steps_per_tick; /* max MCTS steps a game may take per tick without needing the net; 0 = 16      */
+    uint64_t seed;          /* Philox stream for move sampling and Dirichlet noise                           */
+    char start_fen[64];     /* "" = STARTING_GAME_POSITION (self_play_client.cpp:23)                         */
+} az_pool_config;
+
+typedef struct {
+    uint64_t ticks;            /* tree-kernel launches                                            */
+    uint64_t steps;            /* MCTS::step() equivalents                                        */
+    uint64_t evals;            /* leaf evaluations requested from the net                         */
+    uint64_t terminal_steps;   /* steps that ended in an adjudicated leaf (no evaluation)         */
+    uint64_t positions;        /* plies recorded (len(entry["moves"]) summed over all games)     */
+    uint64_t games_finished;   /* games with result 1 or 2                                        */
+    uint64_t games_skipped;    /* games that hit max_plies with result 0 (self_play_client.cpp:628-631) */
+    uint64_t max_depth;        /* deepest selection path seen                                     */
+    uint64_t kernel_launches;  /* kernels launched by the pool                                    */
+    double   net_seconds;      /* device time in the net kernel (CUDA events; 0 if not measured)  */
+    double   tree_seconds;     /* device time in the tree kernel                                  */
+} az_pool_stats;
+
+int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_pool **out);
+void az_pool_destroy(az_pool *pool);
+int az_pool_stats_get(az_pool *pool, az_pool_stats *out);
+
+/* MCTS(thread_id, board, use_dirichlet_noise) ctor (self_play_client.cpp:375-384): reset tree `game` to `root` */
+int az_pool_set_root(az_pool *pool, int game, const az_position *root);
+/* Advance every tree with the internal net until each has root visits >= cfg.visits (search mode) or
+ * `max_ticks` ticks have run.  *idle_out = 1 when no tree needs more work. */
+int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out);
+/* External evaluator (the legacy contract): advance trees until each is blocked on an evaluation or done;
+ * writes float features [n][7][7][4] for the n pending requests (n <= games). */
+int az_pool_collect(az_pool *pool, float *features, int32_t *n_requests);
+/* ... and hand back logits [n][833] / values [n] in the same order (complete_workload semantics). */
+int az_pool_provide(az_pool *pool, const float *logits, const float *values);
+/* root statistics in reference movegen order (visits[i] = edge_visits or 0 when no edge exists) */
+int az_pool_root(az_pool *pool, int game, az_position *pos, int32_t *n_moves, az_move *moves, int32_t *visits,
+                 double *total_score, double *prior, int32_t *root_visits, double *root_value);
+/* MCTS::play(move) (self_play_client.cpp:475-492): re-root on the child (subtree kept) or rebuild */
+int az_pool_play(az_pool *pool, int game, az_move move);
+
+/* Self-play generation (generate_game + Worker::thread_main, self_play_client.cpp:508-645): runs until
+ * `target_games` finished games have been appended to `output_path` as reference-format JSON lines,
+ * `target_positions` plies were recorded or `max_seconds` passed (0 = no limit on that axis). */
+int az_selfplay_run(az_pool *pool, const char *output_path, int64_t target_games, int64_t target_positions,
+                    double max_seconds, az_pool_stats *stats_out);
+
+/* ---------------- legacy 4-function ABI (link.py:8-32; self_play_client.cpp:683,708,723,740) -------- */
+/* Same names, arguments and blocking behaviour.  The trees live on GPU 0 (or $AZ_DEVICE); the caller is
+ * the evaluator: get_workload() fills fill_buffer{1,2} with `buffer_entries` feature planes and returns the
+ * buffer index, complete_workload() takes the matching logits/values.  thread_count must be 2*buffer_entries. */
+void launch_threads(char *output_path, int visits, float *fill_buffer1, float *fill_buffer2, int buffer_entries,
+                    int thread_count);
+int get_workload(void);
+void complete_workload(int workload, float *posteriors, float *values);
+void shutdown(void);
+
 #ifdef __cplusplus
 }
 #endif

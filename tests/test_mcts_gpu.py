@@ -1,0 +1,151 @@
+"""GPU parity of the device-resident PUCT search (through the C ABI) against the reference's own
+search core (goldens produced by oracle/_ref) and the CPU oracle, fed identical fp32 evaluations
+through the external-evaluator contract.  Visit distributions and edge scores must be BIT-EXACT."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def unpack(m):
+    return (m & 0xff, m >> 8)
+
+
+def probe(oracle):
+    def fn(feats):
+        return oracle.probe_eval(feats)
+    return fn
+
+
+def uniform(feats):
+    return np.zeros((len(feats), 833), dtype=np.float32), np.zeros(len(feats), dtype=np.float32)
+
+
+def test_search_goldens_bit_exact(ctx, oracle):
+    """Every reference search in the golden file, all trees advanced concurrently in ONE pool."""
+    from ataxxzero_b200 import rules, search
+    g = load_golden("mcts_golden.json")
+    for ev, fn in (("probe", probe(oracle)), ("uniform", uniform)):
+        for visits in (50, 400, 800, 5000):
+            cases = [s for s in g["searches"] if s["evaluator"] == ev and s["visits"] == visits]
+            if not cases:
+                continue
+            with search.Pool(ctx, len(cases), visits, eval_mode=search.EVAL_EXTERNAL) as pool:
+                for i, s in enumerate(cases):
+                    pool.set_root(i, rules.set_board(s["fen"]))
+                pool.run_external(fn)
+                for i, s in enumerate(cases):
+                    r = pool.root(i)
+                    assert [rules.pack_move(m) for m in r["moves"]] == s["moves"]
+                    assert r["visits"] == s["edge_visits"], (ev, s["fen"], visits)
+                    assert [float(w).hex() for w in r["total_score"]] == s["edge_total_hex"]
+                    assert r["root_visits"] == visits
+
+
+def test_eval_counts_and_priors_match(ctx, oracle):
+    from ataxxzero_b200 import rules, search
+    with search.Pool(ctx, 1, 400, eval_mode=search.EVAL_EXTERNAL) as pool:
+        pool.set_root(0, rules.set_board(rules.START_FEN))
+        pool.run_external(probe(oracle))
+        st = pool.stats()
+        assert st["evals"] == 401 and st["steps"] == 400          # 401 evaluations
+        r = pool.root(0)
+        tree = oracle.tree(oracle.set_board(rules.START_FEN), "probe")
+        tree.search(400)
+        want = tree.dist()
+        mism = sum(float(a).hex() != float(b[3]).hex() for a, b in zip(r["prior"], want))
+        assert mism == 0, "%d of %d root priors differ in the last bit" % (mism, len(want))
+
+
+def test_game_goldens_with_tree_reuse(ctx, oracle):
+    """Whole games (search, play most-visited, re-root with the kept subtree) against the reference."""
+    from ataxxzero_b200 import rules, search
+    g = load_golden("mcts_golden.json")
+    for game in g["games"]:
+        fn = probe(oracle) if game["evaluator"] == "probe" else uniform
+        with search.Pool(ctx, 1, game["visits"], eval_mode=search.EVAL_EXTERNAL) as pool:
+            pool.set_root(0, rules.set_board(game["fen"]))
+            for k, ply in enumerate(game["plies"]):
+                pool.run_external(fn)
+                r = pool.root(0)
+                assert r["visits"] == ply["visits"], (game["evaluator"], game["visits"], k)
+                pool.play(0, unpack(ply["played"]))
+            final = pool.root(0)["position"]
+            assert int(rules.result_batch(ctx, [final])[0]) == game["result"]
+            # the reference re-evaluates the new root after every play() that does not end the game
+            # (self_play_client.cpp:489-490); we keep the stored priors instead, so we ask for fewer evaluations
+            replays = len(game["plies"]) - (1 if game["result"] != 0 else 0)
+            assert pool.stats()["evals"] == game["evals"] - replays
+
+
+def test_many_trees_concurrently_vs_oracle(ctx, oracle):
+    """256 different roots searched at once; each tree must equal the oracle's sequential search."""
+    import random
+    from ataxxzero_b200 import rules, search
+    rng = random.Random(5)
+    roots = []
+    while len(roots) < 256:
+        p = oracle.set_board(rules.START_FEN)
+        for _ in range(rng.randrange(0, 90)):
+            mv = oracle.movegen(p)
+            if not mv or oracle.result(p):
+                break
+            p = oracle.makemove(p, rng.choice(mv))
+        if oracle.result(p) == 0:
+            roots.append(p)
+    with search.Pool(ctx, 256, 120, eval_mode=search.EVAL_EXTERNAL) as pool:
+        for i, p in enumerate(roots):
+            q = rules.Position()
+            q.ply, q.turn, q.blockers = p.ply, p.turn, p.blockers
+            q.pieces[0], q.pieces[1] = p.pieces[0], p.pieces[1]
+            pool.set_root(i, q)
+        pool.run_external(probe(oracle))
+        for i in range(0, 256, 5):
+            tree = oracle.tree(roots[i], "probe")
+            tree.search(120)
+            want = tree.dist()
+            r = pool.root(i)
+            assert r["visits"] == [w[1] for w in want]
+            assert [float(x).hex() for x in r["total_score"]] == [float(w[2]).hex() for w in want]
+            tree.close()
+
+
+def test_internal_net_search_matches_external_feed(ctx):
+    """The fused path (tree kernel -> net kernel on device) equals feeding the same net's outputs through
+    the external contract: the net is deterministic and batch-invariant."""
+    from ataxxzero_b200 import model, net, rules, search
+    network = model.Network.random_init(seed=3)
+    net.load_weights(ctx, network)
+    fen = load_golden("mcts_golden.json")["midgame_fen"]
+    for mode in (search.EVAL_FP32, search.EVAL_BF16):
+        with search.Pool(ctx, 3, 200, eval_mode=mode) as a, search.Pool(ctx, 3, 200, eval_mode=search.EVAL_EXTERNAL) as b:
+            for i, f in enumerate((rules.START_FEN, rules.OPEN_FEN, fen)):
+                a.set_root(i, rules.set_board(f))
+                b.set_root(i, rules.set_board(f))
+            assert a.run()
+            b.run_external(lambda feats: tuple(x.reshape(len(feats), -1) for x in net.forward(ctx, feats, mode)))
+            for i in range(3):
+                assert a.root(i)["visits"] == b.root(i)["visits"]
+                assert sum(a.root(i)["visits"]) == 200
+
+
+def test_play_errors_and_rebuild(ctx, oracle):
+    import ataxxzero_b200 as az
+    from ataxxzero_b200 import rules, search
+    with search.Pool(ctx, 1, 30, eval_mode=search.EVAL_EXTERNAL) as pool:
+        pool.set_root(0, rules.set_board(rules.START_FEN))
+        pool.run_external(probe(oracle))
+        with pytest.raises(az.AzError):
+            pool.play(0, (0, 0))                       # a1 is occupied: not a legal move
+        r = pool.root(0)
+        unvisited = [m for m, v in zip(r["moves"], r["visits"]) if v == 0]
+        assert unvisited                               # FPU=0 keeps 30-visit searches narrow (SURVEY B-10)
+        pool.play(0, unvisited[0])                     # miss: the tree is rebuilt from the moved board (:479-483)
+        pool.run_external(probe(oracle))
+        tree = oracle.tree(oracle.set_board(rules.START_FEN), "probe")
+        tree.search(30)
+        tree.play(unvisited[0])
+        tree.search(30)
+        assert pool.root(0)["visits"] == [d[1] for d in tree.dist()]
