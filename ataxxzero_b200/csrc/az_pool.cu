@@ -40,7 +40,7 @@ struct az_pool {
     uint64_t ticks = 0, launches = 0;
     double net_seconds = 0.0, tree_seconds = 0.0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    uint64_t written_games = 0, written_positions = 0;
+    uint64_t written_games = 0, written_positions = 0, d2h_bytes = 0;
 };
 
 namespace {
@@ -140,7 +140,7 @@ std::string record_to_json(const uint32_t *rec, int words, int plies, int result
 }
 
 // copy out finished games, append them to `out` (may be null: records are dropped), release the buffers
-int drain_finished(az_pool *pool, FILE *out, int64_t *games_written)
+int drain_finished(az_pool *pool, FILE *out, int64_t *games_written, bool copy_payload = true)
 {
     cudaStream_t s = pool->ctx->stream;
     AZ_CUDA(cudaMemcpyAsync(pool->h_counts + 1, pool->dev.done_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -154,9 +154,12 @@ int drain_finished(az_pool *pool, FILE *out, int64_t *games_written)
     for (int i = 0; i < n; ++i) {
         const DoneEntry &d = pool->h_done[i];
         const uint32_t *src = pool->dev.records + ((size_t)d.game * 2 + d.buf) * pool->dev.rec_cap_words;
-        AZ_CUDA(cudaMemcpyAsync(pool->h_record, src, sizeof(uint32_t) * d.words, cudaMemcpyDeviceToHost, s));
-        AZ_CUDA(cudaStreamSynchronize(s));
-        if (out) {
+        if (copy_payload) {
+            AZ_CUDA(cudaMemcpyAsync(pool->h_record, src, sizeof(uint32_t) * d.words, cudaMemcpyDeviceToHost, s));
+            AZ_CUDA(cudaStreamSynchronize(s));
+            pool->d2h_bytes += sizeof(uint32_t) * (uint64_t)d.words;
+        }
+        if (out && copy_payload) {
             const std::string line = record_to_json(pool->h_record, d.words, d.plies, d.result);
             if (fwrite(line.data(), 1, line.size(), out) != line.size() || fputc('\n', out) == EOF)
                 return az_fail(AZ_ERR_IO, "short write to the game file");
@@ -280,6 +283,7 @@ extern "C" int az_pool_stats_get(az_pool *pool, az_pool_stats *out)
     }
     s.ticks = pool->ticks;
     s.kernel_launches = pool->launches;
+    s.record_bytes = pool->d2h_bytes;
     s.net_seconds = pool->net_seconds;
     s.tree_seconds = pool->tree_seconds;
     *out = s;
@@ -419,6 +423,35 @@ extern "C" int az_pool_play(az_pool *pool, int game, az_move move)
     return AZ_OK;
 }
 
+namespace {
+const int kTicksPerDrain = 32;
+
+// `ticks` iterations of (tree kernel, net kernel) back to back on the stream, then one drain of finished games
+int run_ticks(az_pool *pool, FILE *out, bool copy_records, int ticks, int64_t *games)
+{
+    cudaStream_t s = pool->ctx->stream;
+    int rc = AZ_OK;
+    for (int t = 0; t < ticks && rc == AZ_OK; ++t) {
+        const bool timed = (t == 0);            // sample the device time of one tick per drain interval
+        if (timed) cudaEventRecord(pool->ev[0], s);
+        rc = launch_tree(pool);
+        if (timed) cudaEventRecord(pool->ev[1], s);
+        if (rc == AZ_OK) rc = launch_net(pool);
+        if (timed) cudaEventRecord(pool->ev[2], s);
+    }
+    if (rc) return rc;
+    if ((rc = drain_finished(pool, out, games, copy_records))) return rc;
+    AZ_CUDA(cudaStreamSynchronize(s));
+    float ms_tree = 0.f, ms_net = 0.f;
+    if (cudaEventElapsedTime(&ms_tree, pool->ev[0], pool->ev[1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms_net, pool->ev[1], pool->ev[2]) == cudaSuccess) {
+        pool->tree_seconds += ms_tree * 1e-3 * ticks;       // extrapolated from the sampled tick
+        pool->net_seconds += ms_net * 1e-3 * ticks;
+    }
+    return AZ_OK;
+}
+}  // namespace
+
 extern "C" int az_selfplay_run(az_pool *pool, const char *output_path, int64_t target_games, int64_t target_positions,
                                double max_seconds, az_pool_stats *stats_out)
 {
@@ -431,34 +464,41 @@ extern "C" int az_selfplay_run(az_pool *pool, const char *output_path, int64_t t
         out = fopen(output_path, "a");            // append mode, like std::ios_base::app (:691)
         if (!out) return az_fail(AZ_ERR_IO, "az_selfplay_run: cannot open '%s' for appending", output_path);
     }
-    cudaStream_t s = pool->ctx->stream;
     const auto t0 = std::chrono::steady_clock::now();
     const uint64_t pos0 = pool->written_positions;
     int64_t games = 0;
     int rc = AZ_OK;
-    const int kTicksPerDrain = 32;
     for (;;) {
-        for (int t = 0; t < kTicksPerDrain && rc == AZ_OK; ++t) {
-            const bool timed = (t == 0);        // sample device time of one tick per drain interval
-            if (timed) cudaEventRecord(pool->ev[0], s);
-            rc = launch_tree(pool);
-            if (timed) cudaEventRecord(pool->ev[1], s);
-            if (rc == AZ_OK) rc = launch_net(pool);
-            if (timed) cudaEventRecord(pool->ev[2], s);
-        }
-        if (rc) break;
-        if ((rc = drain_finished(pool, out, &games))) break;
-        float ms_tree = 0.f, ms_net = 0.f;
-        if (cudaEventElapsedTime(&ms_tree, pool->ev[0], pool->ev[1]) == cudaSuccess &&
-            cudaEventElapsedTime(&ms_net, pool->ev[1], pool->ev[2]) == cudaSuccess) {
-            pool->tree_seconds += ms_tree * 1e-3 * kTicksPerDrain;      // extrapolated from the sampled tick
-            pool->net_seconds += ms_net * 1e-3 * kTicksPerDrain;
-        }
+        if ((rc = run_ticks(pool, out, true, kTicksPerDrain, &games))) break;
         const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (target_games > 0 && games >= target_games) break;
         if (target_positions > 0 && (int64_t)(pool->written_positions - pos0) >= target_positions) break;
         if (max_seconds > 0 && elapsed >= max_seconds) break;
         if ((pool->ticks & 1023) < (uint64_t)kTicksPerDrain && (rc = check_game_errors(pool))) break;
+    }
+    if (out) fclose(out);
+    if (rc) return rc;
+    if ((rc = check_game_errors(pool))) return rc;
+    if (stats_out) return az_pool_stats_get(pool, stats_out);
+    return AZ_OK;
+}
+
+extern "C" int az_selfplay_ticks(az_pool *pool, const char *output_path, int64_t ticks, az_pool_stats *stats_out)
+{
+    AZ_REQUIRE(pool && ticks >= 0, AZ_ERR_ARG, "az_selfplay_ticks: bad argument");
+    AZ_REQUIRE(pool->cfg.auto_play, AZ_ERR_STATE, "az_selfplay_ticks: pool was created with auto_play = 0");
+    AZ_REQUIRE(pool->cfg.eval_mode != AZ_EVAL_EXTERNAL, AZ_ERR_STATE, "az_selfplay_ticks: external evaluator pools are driven by collect/provide");
+    FILE *out = nullptr;
+    if (output_path && output_path[0]) {
+        out = fopen(output_path, "a");
+        if (!out) return az_fail(AZ_ERR_IO, "az_selfplay_ticks: cannot open '%s' for appending", output_path);
+    }
+    int rc = AZ_OK;
+    int64_t games = 0;
+    for (int64_t done = 0; done < ticks && rc == AZ_OK;) {
+        const int chunk = (int)std::min<int64_t>(kTicksPerDrain, ticks - done);
+        rc = run_ticks(pool, out, out != nullptr, chunk, &games);
+        done += chunk;
     }
     if (out) fclose(out);
     if (rc) return rc;

@@ -25,7 +25,8 @@ class PoolConfig(C.Structure):
 class PoolStats(C.Structure):
     _fields_ = [("ticks", C.c_uint64), ("steps", C.c_uint64), ("evals", C.c_uint64), ("terminal_steps", C.c_uint64),
                 ("positions", C.c_uint64), ("games_finished", C.c_uint64), ("games_skipped", C.c_uint64),
-                ("max_depth", C.c_uint64), ("kernel_launches", C.c_uint64), ("net_seconds", C.c_double),
+                ("max_depth", C.c_uint64), ("kernel_launches", C.c_uint64), ("record_bytes", C.c_uint64),
+                ("net_seconds", C.c_double),
                 ("tree_seconds", C.c_double)]
 
     def as_dict(self):
@@ -44,6 +45,7 @@ _native.register("az_pool_root", C.c_int, [_vp, C.c_int, C.POINTER(Position), C.
                                            C.POINTER(C.c_int32), C.POINTER(C.c_double)])
 _native.register("az_pool_play", C.c_int, [_vp, C.c_int, C.c_uint16])
 _native.register("az_selfplay_run", C.c_int, [_vp, C.c_char_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(PoolStats)])
+_native.register("az_selfplay_ticks", C.c_int, [_vp, C.c_char_p, C.c_int64, C.POINTER(PoolStats)])
 
 
 class Pool:
@@ -141,6 +143,13 @@ class Pool:
         path = output_path.encode() if output_path else None
         check(lib().az_selfplay_run(self._h, path, int(target_games), int(target_positions), float(max_seconds),
                                     C.byref(stats)))
+        return stats.as_dict()
+
+    def selfplay_ticks(self, ticks, output_path=None):
+        """Exactly ``ticks`` tree+net iterations; records go to ``output_path`` or stay on the device."""
+        stats = PoolStats()
+        path = output_path.encode() if output_path else None
+        check(lib().az_selfplay_ticks(self._h, path, int(ticks), C.byref(stats)))
         return stats.as_dict()
 
     def stats(self):

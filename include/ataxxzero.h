@@ -147,6 +147,7 @@ typedef struct {
     uint64_t games_skipped;    /* games that hit max_plies with result 0 (self_play_client.cpp:628-631) */
     uint64_t max_depth;        /* deepest selection path seen                                     */
     uint64_t kernel_launches;  /* kernels launched by the pool                                    */
+    uint64_t record_bytes;     /* game-record bytes copied device -> host                         */
     double   net_seconds;      /* device time in the net kernel (CUDA events; 0 if not measured)  */
     double   tree_seconds;     /* device time in the tree kernel                                  */
 } az_pool_stats;
@@ -176,6 +177,10 @@ int az_pool_play(az_pool *pool, int game, az_move move);
  * `target_positions` plies were recorded or `max_seconds` passed (0 = no limit on that axis). */
 int az_selfplay_run(az_pool *pool, const char *output_path, int64_t target_games, int64_t target_positions,
                     double max_seconds, az_pool_stats *stats_out);
+
+/* Fixed amount of work instead of a target: exactly `ticks` (tree kernel + net kernel) iterations.  With
+ * output_path = NULL finished games are recycled on the device and their records are not copied out. */
+int az_selfplay_ticks(az_pool *pool, const char *output_path, int64_t ticks, az_pool_stats *stats_out);
 
 /* ---------------- legacy 4-function ABI (link.py:8-32; self_play_client.cpp:683,708,723,740) -------- */
 /* Same names, arguments and blocking behaviour.  The trees live on GPU 0 (or $AZ_DEVICE); the caller is

@@ -629,6 +629,11 @@ void ao_probe_eval(void *ctx, const float feats[AO_FEATURES], float logits[AO_LO
     *value = (float)((double)(h & 0xffffff) / (double)0x1000000 * 1.6 - 0.8);
 }
 
+void ao_probe_eval_batch(const float *feats, int n, float *logits, float *values)
+{
+    for (int i = 0; i < n; i++) ao_probe_eval(NULL, feats + (size_t)i * AO_FEATURES, logits + (size_t)i * AO_LOGITS, values + i);
+}
+
 void ao_uniform_eval(void *ctx, const float feats[AO_FEATURES], float logits[AO_LOGITS], float *value)
 {
     (void)ctx; (void)feats;

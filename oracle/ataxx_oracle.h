@@ -88,6 +88,7 @@ long     ao_mcts_tie_count(const ao_mcts *m);              /* #select_action cal
 /* The deterministic probe evaluator of SURVEY App. D (FNV-style hash of the 196
  * feature non-zero flags -> 833 logits in [-2,2), value in [-0.8,0.8)). */
 void ao_probe_eval(void *ctx, const float feats[AO_FEATURES], float logits[AO_LOGITS], float *value);
+void ao_probe_eval_batch(const float *feats, int n, float *logits, float *values);
 /* Degenerate evaluator: all logits 0, value 0 -> every prior ties (exercises map order). */
 void ao_uniform_eval(void *ctx, const float feats[AO_FEATURES], float logits[AO_LOGITS], float *value);
 

@@ -171,13 +171,10 @@ class Oracle(_Base):
         feats = np.ascontiguousarray(feats, dtype=np.float32).reshape(-1, 196)
         logits = np.zeros((feats.shape[0], 833), dtype=np.float32)
         values = np.zeros(feats.shape[0], dtype=np.float32)
-        fn = self.lib.ao_probe_eval
+        fn = self.lib.ao_probe_eval_batch
         fn.restype = None
-        fn.argtypes = [C.c_void_p, _f32p, _f32p, _f32p]
-        for i in range(feats.shape[0]):
-            v = C.c_float()
-            fn(None, feats[i].ctypes.data_as(_f32p), logits[i].ctypes.data_as(_f32p), C.byref(v))
-            values[i] = v.value
+        fn.argtypes = [_f32p, C.c_int, _f32p, _f32p]
+        fn(feats.ctypes.data_as(_f32p), feats.shape[0], logits.ctypes.data_as(_f32p), values.ctypes.data_as(_f32p))
         return logits, values
 
     def search(self, fen, visits, evaluator="probe"):

@@ -262,3 +262,30 @@ def test_live_umap_order(oracle, reference):
         b, bb = reference.umap_order(mo)
         assert a == b and ab == bb
         assert oracle.umap_order(mo, ab)[0] == reference.umap_order(mo, True)[0]
+
+
+def test_torch_cpu_net_matches_numpy_restatement():
+    """The torch-CPU forward used by bench.py's reference arm is the same function as the NumPy oracle."""
+    from oracle import net_numpy, net_torch
+    conv, bn = net_numpy.init_weights(seed=0)
+    bn = net_numpy.randomize_bn(bn)
+    feats = net_numpy.random_features(6, seed=2)
+    want_p, want_v = net_numpy.forward(feats, conv, bn, dtype=np.float64)
+    got_p, got_v = net_torch.TorchNet(conv, bn).forward(feats)
+    assert got_p.shape == (6, 7, 7, 17) and got_v.shape == (6, 1)
+    assert np.abs(got_p - want_p).max() < 1e-5 and np.abs(got_v - want_v).max() < 1e-5
+
+
+def test_weight_file_layout_roundtrip(tmp_path):
+    """model.py:179-196: np.save(path, [conv_list, bn_list]) / np.load(allow_pickle=True)."""
+    from oracle import net_numpy
+    from ataxxzero_b200 import model
+    conv, bn = net_numpy.init_weights(seed=4)
+    path = str(tmp_path / "m.npy")
+    net_numpy.save_model(path, conv, bn)
+    a = model.Network.load(path)                      # product loader reads the oracle-written file
+    assert a.filters == 128 and a.blocks == 12 and a.total_parameters == 3545906
+    a.save(str(tmp_path / "n.npy"))
+    conv2, bn2 = net_numpy.load_model(str(tmp_path / "n.npy"))      # and the other way round
+    assert all(np.array_equal(x, y) for x, y in zip(conv, conv2)) and all(np.array_equal(x, y) for x, y in zip(bn, bn2))
+    assert a.packed().size == 3545906 + 50 * 128

@@ -1,0 +1,112 @@
+"""GPU self-play generation through the C ABI: JSON-lines records in the reference's format
+(self_play_client.cpp:508-582,638-643), every game replayed move by move through the oracle,
+plus the legacy 4-function contract of link.py driven like accelerated_generate_games.py:54-83."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def replay_and_check(oracle, line, visits):
+    from oracle.cpu import START_FEN
+    game = json.loads(line)
+    assert list(game.keys()) == ["boards", "dists", "moves", "result"]          # nlohmann emits sorted keys
+    assert len(game["boards"]) == len(game["moves"]) == len(game["dists"]) >= 1
+    assert game["result"] in (1, 2)
+    p = oracle.set_board(START_FEN)
+    for board, move, dist in zip(game["boards"], game["moves"], game["dists"]):
+        assert oracle.result(p) == 0
+        assert board == oracle.board_json(p)                                     # blockers serialise as 0 (App. B-1)
+        legal = {oracle.move_string(m): m for m in oracle.movegen(p)}
+        assert move in legal and move in dist
+        assert set(dist) <= set(legal) and list(dist) == sorted(dist)
+        total = sum(dist.values())
+        assert abs(total - 1.0) < 1e-9
+        counts = [w * max(visits, 1) for w in dist.values()]
+        assert all(w > 0 for w in dist.values())
+        p = oracle.makemove(p, legal[move])
+    assert oracle.result(p) == game["result"] or len(game["moves"]) == 400
+    return len(game["moves"])
+
+
+def test_selfplay_records_replay_legally(tmp_path, ctx, oracle):
+    from ataxxzero_b200 import model, net, search
+    net.load_weights(ctx, model.Network.random_init(seed=0))
+    out = str(tmp_path / "model-001-0.json")
+    with search.Pool(ctx, 64, 40, eval_mode=search.EVAL_BF16, noise=True, auto_play=True, seed=7) as pool:
+        stats = pool.selfplay(out, target_games=24, max_seconds=240)
+    lines = open(out).read().splitlines()
+    assert len(lines) >= 24 and stats["games_finished"] >= 24
+    plies = [replay_and_check(oracle, ln, 40) for ln in lines]
+    assert sum(plies) <= stats["positions"]
+    assert stats["evals"] > 0 and stats["steps"] >= stats["evals"] - stats["positions"] - 64
+    # append mode (std::ios_base::app, :691): a second run adds to the same file
+    with search.Pool(ctx, 32, 20, eval_mode=search.EVAL_FP32, noise=True, auto_play=True, seed=8) as pool:
+        pool.selfplay(out, target_games=4, max_seconds=240)
+    assert len(open(out).read().splitlines()) >= len(lines) + 4
+
+
+def test_selfplay_noise_changes_games_and_seed_reproduces(tmp_path, ctx):
+    from ataxxzero_b200 import model, net, search
+    net.load_weights(ctx, model.Network.random_init(seed=0))
+
+    def run(seed, name):
+        out = str(tmp_path / name)
+        with search.Pool(ctx, 8, 30, eval_mode=search.EVAL_BF16, noise=True, auto_play=True, seed=seed) as pool:
+            pool.selfplay_ticks(600, out)
+        return sorted(open(out).read().splitlines()) if os.path.exists(out) else []
+    a, b, c = run(1, "a.json"), run(1, "b.json"), run(2, "c.json")
+    assert a and a == b            # same seed -> same games (Philox streams are per game slot)
+    assert a != c
+
+
+def test_visit_targets_respected(tmp_path, ctx, oracle):
+    """Each recorded distribution is n/N with N >= visits at the moment the move was chosen."""
+    from ataxxzero_b200 import model, net, search
+    net.load_weights(ctx, model.Network.random_init(seed=0))
+    out = str(tmp_path / "g.json")
+    with search.Pool(ctx, 16, 64, eval_mode=search.EVAL_BF16, noise=False, auto_play=True, seed=3) as pool:
+        pool.selfplay(out, target_games=4, max_seconds=240)
+    for ln in open(out).read().splitlines():
+        for dist in json.loads(ln)["dists"]:
+            smallest = min(dist.values())
+            n_total = round(1.0 / smallest) if smallest > 0 else 0
+            # smallest weight is k/N for some integer k >= 1, so N >= 1/smallest only if k == 1; check weights are multiples of 1/N
+            assert any(all(abs(w * N - round(w * N)) < 1e-6 for w in dist.values()) for N in range(64, 64 + 400))
+
+
+def test_legacy_link_contract(tmp_path, ctx, oracle):
+    """accelerated_generate_games.py's loop, verbatim, on top of ataxxzero_b200.link."""
+    import ctypes
+    from ataxxzero_b200 import link, model, net
+    net.load_weights(ctx, model.Network.random_init(seed=0))
+    out = str(tmp_path / "legacy.json")
+    buffer_size = 16
+    work_buffers = [np.zeros((buffer_size, 7, 7, 4), dtype=np.float32) for _ in (0, 1)]
+    link.launch_threads(out.encode("utf-8"), 24, ctypes.c_void_p(work_buffers[0].ctypes.data),
+                        ctypes.c_void_p(work_buffers[1].ctypes.data), buffer_size, buffer_size * 2)
+    try:
+        for _ in range(6000):
+            i = link.get_workload()
+            features = work_buffers[i]
+            assert features[..., 0].min() == 1.0                       # plane 0 is all ones
+            posteriors, values = net.forward(ctx, features, net.BF16)
+            assert posteriors.dtype == np.float32 and posteriors.flags.c_contiguous
+            link.complete_workload(i, ctypes.c_void_p(posteriors.ctypes.data), ctypes.c_void_p(values.ctypes.data))
+            if os.path.exists(out) and os.path.getsize(out) > 0 and open(out).read().count("\n") >= 3:
+                break
+    finally:
+        link.shutdown()
+    lines = open(out).read().splitlines()
+    assert len(lines) >= 3
+    for ln in lines:
+        replay_and_check(oracle, ln, 24)
+    # shutdown clears the globals: a second launch must work (self_play_client.cpp:744-748)
+    link.launch_threads(out.encode("utf-8"), 8, ctypes.c_void_p(work_buffers[0].ctypes.data),
+                        ctypes.c_void_p(work_buffers[1].ctypes.data), buffer_size, buffer_size * 2)
+    i = link.get_workload()
+    assert i in (0, 1)
+    link.shutdown()
