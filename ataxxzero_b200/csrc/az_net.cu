@@ -151,13 +151,6 @@ __global__ void k_i8_to_f32(const int8_t *in, float *out, size_t n)
     if (i < n) out[i] = (float)in[i];
 }
 
-int upload(float **dst, const float *src, size_t count)
-{
-    AZ_CUDA(cudaMalloc(dst, sizeof(float) * count));
-    AZ_CUDA(cudaMemcpy(*dst, src, sizeof(float) * count, cudaMemcpyHostToDevice));
-    return AZ_OK;
-}
-
 }  // namespace
 
 extern "C" size_t az_net_param_count(int filters, int blocks)
@@ -171,11 +164,30 @@ void az_net_release(az_context *ctx)
     AzNet *n = ctx->net;
     if (!n) return;
     az_net_tc_release(n);
-    for (float *p : {n->w_in, n->w_tower, n->bn_mean, n->bn_scale, n->w_policy, n->w_value, n->fc_w, n->fc_b})
+    for (float *p : {n->packed, n->bn_mean, n->bn_scale})
         if (p) cudaFree(p);
+    if (n->d_flag) cudaFree(n->d_flag);
     delete n;
     ctx->net = nullptr;
 }
+
+namespace {
+// inference batch-norm constants: scale = 1/sqrt(var + eps) (computed in double), and a finiteness check of
+// every parameter (a NaN/Inf weight is an argument error, not something to discover 25 layers later)
+__global__ void k_prepare_bn(const float *__restrict__ packed, size_t count, const float *__restrict__ bn, int layers, int f,
+                             float *__restrict__ mean, float *__restrict__ scale, int *__restrict__ flag)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count && !isfinite(packed[i])) atomicOr(flag, 1);
+    if (i < (size_t)layers * f) {
+        const int l = (int)(i / f), c = (int)(i % f);
+        const float var = bn[(size_t)(2 * l + 1) * f + c];
+        if (!(var + AZ_BN_EPS > 0.f)) atomicOr(flag, 2);
+        mean[i] = bn[(size_t)(2 * l) * f + c];
+        scale[i] = (float)(1.0 / sqrt((double)var + (double)AZ_BN_EPS));
+    }
+}
+}  // namespace
 
 extern "C" int az_net_load(az_context *ctx, const float *packed, size_t count, int filters, int blocks)
 {
@@ -185,43 +197,52 @@ extern "C" int az_net_load(az_context *ctx, const float *packed, size_t count, i
     AZ_REQUIRE(count == az_net_param_count(filters, blocks), AZ_ERR_ARG,
                "az_net_load: expected %zu floats for filters=%d blocks=%d, got %zu", az_net_param_count(filters, blocks),
                filters, blocks, count);
-    for (size_t i = 0; i < count; ++i)
-        AZ_REQUIRE(std::isfinite(packed[i]), AZ_ERR_ARG, "az_net_load: non-finite weight at index %zu", i);
-    az_net_release(ctx);
-    AzNet *net = new AzNet();
-    ctx->net = net;
-    net->filters = filters;
-    net->blocks = blocks;
-    net->layers = 1 + 2 * blocks;
+    AzNet *net = ctx->net;
+    if (net && (net->filters != filters || net->blocks != blocks)) {
+        AZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        az_net_release(ctx);
+        net = nullptr;
+    }
     const size_t f = (size_t)filters;
-    const float *p = packed;
-    int rc;
-    if ((rc = upload(&net->w_in, p, 9 * 4 * f))) return rc;
-    p += 9 * 4 * f;
-    if ((rc = upload(&net->w_tower, p, (size_t)2 * blocks * 9 * f * f))) return rc;
-    p += (size_t)2 * blocks * 9 * f * f;
-    if ((rc = upload(&net->w_policy, p, f * 17))) return rc;
-    p += f * 17;
-    if ((rc = upload(&net->w_value, p, f))) return rc;
-    p += f;
-    if ((rc = upload(&net->fc_w, p, 49))) return rc;
-    p += 49;
-    if ((rc = upload(&net->fc_b, p, 1))) return rc;
-    p += 1;
-    std::vector<float> mean((size_t)net->layers * f), scale((size_t)net->layers * f);
-    for (int l = 0; l < net->layers; ++l)
-        for (size_t c = 0; c < f; ++c) {
-            const float var = p[(size_t)(2 * l + 1) * f + c];
-            AZ_REQUIRE(var + AZ_BN_EPS > 0.f, AZ_ERR_ARG, "az_net_load: batch-norm variance %g at layer %d", var, l);
-            mean[l * f + c] = p[(size_t)(2 * l) * f + c];
-            scale[l * f + c] = (float)(1.0 / std::sqrt((double)var + (double)AZ_BN_EPS));
-        }
-    if ((rc = upload(&net->bn_mean, mean.data(), mean.size()))) return rc;
-    if ((rc = upload(&net->bn_scale, scale.data(), scale.size()))) return rc;
-    std::vector<float> host(packed, packed + count);
-    if ((rc = az_net_tc_prepare(ctx, net, host))) return rc;
-    AZ_CUDA(cudaFuncSetAttribute(k_net_fp32<AZ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FP32));
-    AZ_CUDA(cudaFuncSetAttribute(k_net_fp32<AZ_IN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FP32));
+    if (!net) {                                  // first load of this shape: allocate once, reuse on every reload
+        net = new AzNet();
+        ctx->net = net;
+        net->filters = filters;
+        net->blocks = blocks;
+        net->layers = 1 + 2 * blocks;
+        AZ_CUDA(cudaMalloc(&net->packed, sizeof(float) * count));
+        AZ_CUDA(cudaMalloc(&net->bn_mean, sizeof(float) * net->layers * f));
+        AZ_CUDA(cudaMalloc(&net->bn_scale, sizeof(float) * net->layers * f));
+        AZ_CUDA(cudaMalloc(&net->d_flag, sizeof(int)));
+        float *p = net->packed;
+        net->w_in = p;                      p += 9 * 4 * f;
+        net->w_tower = p;                   p += (size_t)2 * blocks * 9 * f * f;
+        net->w_policy = p;                  p += f * 17;
+        net->w_value = p;                   p += f;
+        net->fc_w = p;                      p += 49;
+        net->fc_b = p;                      p += 1;
+        net->bn_raw = p;
+        int rc = az_net_tc_alloc(net);
+        if (rc) return rc;
+        AZ_CUDA(cudaFuncSetAttribute(k_net_fp32<AZ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FP32));
+        AZ_CUDA(cudaFuncSetAttribute(k_net_fp32<AZ_IN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FP32));
+    }
+    cudaStream_t s = ctx->stream;
+    AZ_CUDA(cudaMemcpyAsync(net->packed, packed, sizeof(float) * count, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaMemsetAsync(net->d_flag, 0, sizeof(int), s));
+    k_prepare_bn<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(net->packed, count, net->bn_raw, net->layers, filters, net->bn_mean,
+                                                                 net->bn_scale, net->d_flag);
+    int rc = az_net_tc_prepare(ctx, net);        // bf16 re-tiling with the BN scale folded in, on the device
+    if (rc) return rc;
+    ctx->launches += 4;
+    int flag = 0;
+    AZ_CUDA(cudaMemcpyAsync(&flag, net->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    AZ_CUDA(cudaGetLastError());
+    if (flag) {
+        az_net_release(ctx);
+        return az_fail(AZ_ERR_ARG, flag & 1 ? "az_net_load: non-finite weight" : "az_net_load: batch-norm variance + eps <= 0");
+    }
     return AZ_OK;
 }
 

@@ -4,10 +4,16 @@
 #include <cuda_bf16.h>
 
 constexpr int AZ_F = 128;            // filters (model.py:16)
-constexpr float AZ_BN_EPS = 1e-3f;   // tf.layers.batch_normalization default epsilon
+constexpr float AZ_BN_EPS = 1e-3f;
+#ifndef AZ_NET_TILES_DEFAULT
+#define AZ_NET_TILES_DEFAULT 1
+#endif   // tf.layers.batch_normalization default epsilon
 
 struct AzNet {
     int filters = 0, blocks = 0, layers = 0;   // layers = 1 + 2*blocks convolutions with batch-norm
+    float *packed = nullptr;     // the caller's parameter vector, verbatim (everything below points into it)
+    float *bn_raw = nullptr;     // [layers][2][F] moving mean / variance as stored in the .npy
+    int *d_flag = nullptr;       // validation flag written by the prepare kernels
     // fp32 mode: weights in TF order [layer][tap = kh*3+kw][cin][cout]; layer 0 has cin = 4
     float *w_in = nullptr;       // [9][4][F]
     float *w_tower = nullptr;    // [2*blocks][9][F][F]
@@ -18,6 +24,8 @@ struct AzNet {
     float *fc_w = nullptr;       // [49]
     float *fc_b = nullptr;       // [1]
     // bf16 tensor-core mode (az_net_tc.cu): BN scale folded into the weights, UMMA operand layout
+    uint8_t *tc_stream = nullptr;      // [input conv | tower | heads] in the order the TMA producer streams them
+    int tc_tiles = 2;                  // kernel variant: tiles (of 2 boards) per CTA
     __nv_bfloat16 *tc_w = nullptr;     // [2*blocks][18 chunks][8 kgroups][128 cout][8 cin]
     float *tc_shift = nullptr;         // [layers][F]   -mean * scale
     __nv_bfloat16 *tc_w_in = nullptr;  // [5 k-steps][2 k-groups = taps][128 cout][8 cin (4 real)] bf16, scale folded
@@ -25,7 +33,8 @@ struct AzNet {
 };
 
 // az_net_tc.cu
-int az_net_tc_prepare(az_context *ctx, AzNet *net, const std::vector<float> &host_packed);
+int az_net_tc_alloc(AzNet *net);
+int az_net_tc_prepare(az_context *ctx, AzNet *net);
 int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
                       const int *d_count = nullptr);
 // internal: forward over up to `n` boards; when d_count != nullptr the actual count is read on the device

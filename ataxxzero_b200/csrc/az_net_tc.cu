@@ -22,50 +22,54 @@
 #include "az_net.h"
 #include "az_rules.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace {
 
 constexpr int F = AZ_F;                  // channels
 constexpr int KG = F / 8;                // 16 k-groups of 8 channels
 constexpr int TILE_M = 128;              // GEMM rows per tile (2 boards x 64)
-constexpr int TILES = 2;                 // tiles per CTA unit
-constexpr int UNIT_BOARDS = 2 * TILES;   // 4
 constexpr int MARGIN = 16;               // zero rows before/after the tiles (shifts reach +-9)
-constexpr int ACT_ROWS = MARGIN + TILES * TILE_M + MARGIN;     // 288
 constexpr int ROW_BYTES = 16;            // 8 bf16
-constexpr int ACT_LBO = ACT_ROWS * ROW_BYTES;                  // bytes between k-groups of the A operand
-constexpr int ACT_BYTES = KG * ACT_LBO;                        // 73728
 constexpr int STAGES = 4;
 constexpr int STAGE_BYTES = 8 * F * ROW_BYTES;                 // 8 k-groups x 128 cout x 16 B = 16384
 constexpr int CHUNKS = 18;               // per layer: 2 input-channel halves x 9 taps
 constexpr int W_LBO = F * ROW_BYTES;     // 2048: bytes between k-groups of the B operand
-constexpr int IN_BYTES = ACT_ROWS * ROW_BYTES;                 // input planes: one k-group (4 real + 4 zero channels)
 constexpr int ZERO_BYTES = TILE_M * ROW_BYTES;                 // zero k-group for the padded 10th tap
-constexpr int WIN_BYTES = 5 * 2 * F * ROW_BYTES;               // input conv: 5 k-steps x 2 k-groups x 128 cout
+constexpr int WIN_BYTES = 5 * 2 * F * ROW_BYTES;               // input conv: 5 k-steps x 2 k-groups x 128 cout = 20480
+constexpr int WIN_CHUNK0 = 4 * 2 * F * ROW_BYTES;              // k-steps 0..3 travel as one stage, k-step 4 as a second
 constexpr int HEAD_N = 32;               // 17 policy planes + 1 value plane, padded to a legal UMMA N
 constexpr int WHEAD_BYTES = KG * HEAD_N * ROW_BYTES;           // 8192
 constexpr int HEAD_LBO = HEAD_N * ROW_BYTES;
 
-// shared memory map (bytes)
-constexpr int OFF_ACT = 0;
-constexpr int OFF_RING = OFF_ACT + ACT_BYTES;
-constexpr int OFF_IN = OFF_RING + STAGES * STAGE_BYTES;
-constexpr int OFF_ZERO = OFF_IN + IN_BYTES;
-constexpr int OFF_WIN = OFF_ZERO + ZERO_BYTES;
-constexpr int OFF_WHEAD = OFF_WIN + WIN_BYTES;
-constexpr int OFF_SHIFT = OFF_WHEAD + WHEAD_BYTES;             // float[TILES][2][F]: per-layer BN shifts, double-buffered
-constexpr int OFF_VPART = OFF_SHIFT + TILES * 2 * F * 4;       // float[TILES][4] value-head partial sums
-constexpr int OFF_BAR = OFF_VPART + 64;
-constexpr int NUM_BARS = 2 * STAGES + 2 * TILES + 2;           // full/empty ring, acc_full/act_ready per tile, const loads
-constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16;
-static_assert(SMEM_BYTES < 227 * 1024, "shared memory budget");
-
-constexpr int NUM_WARPS = 2 + 4 * TILES;     // 10
-constexpr int NUM_THREADS = NUM_WARPS * 32;  // 320
-
-// TMEM columns
-constexpr uint32_t TM_ACC = 0;               // + tile*128
-constexpr uint32_t TM_RES = 256;             // + tile*128
+// Per-variant geometry: TILES tiles (2 boards each) per CTA.  TILES = 2 -> one CTA per SM, each weight stage feeds
+// two tiles; TILES = 1 -> two independent CTAs per SM whose epilogues and MMAs interleave on the tensor pipe.
+template <int TILES>
+struct Cfg {
+    static constexpr int UNIT_BOARDS = 2 * TILES;
+    static constexpr int ACT_ROWS = MARGIN + TILES * TILE_M + MARGIN;
+    static constexpr int ACT_LBO = ACT_ROWS * ROW_BYTES;           // bytes between k-groups of the A operand
+    static constexpr int ACT_BYTES = KG * ACT_LBO;
+    static constexpr int IN_BYTES = ACT_ROWS * ROW_BYTES;          // input planes: one k-group (4 real + 4 zero channels)
+    static constexpr int OFF_ACT = 0;
+    static constexpr int OFF_RING = OFF_ACT + ACT_BYTES;
+    static constexpr int OFF_IN = OFF_RING + STAGES * STAGE_BYTES;
+    static constexpr int OFF_ZERO = OFF_IN + IN_BYTES;
+    static constexpr int OFF_SHIFT = OFF_ZERO + ZERO_BYTES;        // float[TILES][2][F]: per-layer BN shifts, double-buffered
+    static constexpr int OFF_VPART = OFF_SHIFT + TILES * 2 * F * 4;
+    static constexpr int OFF_BAR = OFF_VPART + 64;
+    static constexpr int NUM_BARS = 2 * STAGES + 2 * TILES + 1;    // full/empty ring, acc_full/act_ready per tile, input staged
+    static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+    static constexpr int SMEM_BYTES = OFF_TMEM + 16;
+    static constexpr int NUM_WARPS = 2 + 4 * TILES;
+    static constexpr int NUM_THREADS = NUM_WARPS * 32;
+    static constexpr int CTAS_PER_SM = TILES == 1 ? 2 : 1;
+    static constexpr uint32_t TMEM_COLS = TILES * 256;             // per tile: 128 accumulator + 128 residual columns
+    static constexpr uint32_t TM_ACC = 0;                          // + tile*128
+    static constexpr uint32_t TM_RES = TILES * 128;                // + tile*128
+    static_assert(SMEM_BYTES * CTAS_PER_SM + 1024 * CTAS_PER_SM <= 228 * 1024, "shared memory budget");
+};
 
 // instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N
 constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24); }
@@ -182,7 +186,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 }
 
 // named barrier among the 4 epilogue warps of one tile
-__device__ __forceinline__ void group_sync(int tile) { asm volatile("bar.sync %0, 128;" ::"r"(1 + tile) : "memory"); }
+__device__ __forceinline__ void group_sync(int tile)
+{
+    // literal barrier ids so ptxas reserves 3 barriers, not all 16 (two CTAs share an SM in the 1-tile variant)
+    if (tile == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 
 struct TcParams {
     const void *input;                 // float[n][196] or az_position[n]
@@ -190,9 +199,7 @@ struct TcParams {
     const int *n_ptr;                  // when non-null the board count is read from device memory
     int layers;                        // 1 + 2*blocks
     int debug_layers;                  // >= 0: stop after this many conv layers and dump activations
-    const __nv_bfloat16 *w_tower;      // [2*blocks][18][8][128][8]
-    const __nv_bfloat16 *w_in;         // [5][2][128][8]
-    const __nv_bfloat16 *w_heads;      // [16][32][8]
+    const uint8_t *w_stream;           // [input conv 20480 B][2*blocks x 18 chunks x 16384 B][heads 8192 B]
     const float *shift;                // [layers][128]
     const float *fc_w;                 // [49]
     const float *fc_b;                 // [1]
@@ -211,131 +218,129 @@ __device__ __forceinline__ bool row_is_real(int r, int &board_in_tile, int &cell
     return w >= 8 && y != 7;
 }
 
-template <int IN_KIND>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
+template <int TILES, int IN_KIND>
+__global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_SM) k_net_tc(const TcParams P)
 {
+    using C = Cfg<TILES>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    auto bar = [&](int i) { return sbase + OFF_BAR + 8 * i; };
+    auto bar = [&](int i) { return sbase + C::OFF_BAR + 8 * i; };
     // barrier indices
-    const int B_FULL = 0, B_EMPTY = STAGES, B_ACC = 2 * STAGES, B_ACT = 2 * STAGES + TILES, B_CONST = 2 * STAGES + 2 * TILES;
-    const int B_IN = B_CONST + 1;      // input planes staged (arrived by the epilogue threads)
+    constexpr int B_FULL = 0, B_EMPTY = STAGES, B_ACC = 2 * STAGES, B_ACT = 2 * STAGES + TILES, B_IN = 2 * STAGES + 2 * TILES;
 
     const int n_boards = P.n_ptr ? min(*P.n_ptr, P.n) : P.n;
-    const int num_units = (n_boards + UNIT_BOARDS - 1) / UNIT_BOARDS;
+    const int num_units = (n_boards + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS;
     const int tower_layers = P.layers - 1;          // tensor-core 128->128 convs
     const int run_layers = P.debug_layers >= 0 ? min(P.debug_layers, P.layers) : P.layers;   // conv layers executed (incl. input conv)
+    const int nl = min(tower_layers, run_layers - 1);
+    const bool heads = P.debug_layers < 0;
 
     // ---- one-time setup ----
-    for (int i = threadIdx.x; i < (ACT_BYTES + 0) / 16; i += NUM_THREADS) reinterpret_cast<uint4 *>(smem + OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < (IN_BYTES + ZERO_BYTES) / 16; i += NUM_THREADS)
-        reinterpret_cast<uint4 *>(smem + OFF_IN)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < C::ACT_BYTES / 16; i += C::NUM_THREADS) reinterpret_cast<uint4 *>(smem + C::OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (C::IN_BYTES + ZERO_BYTES) / 16; i += C::NUM_THREADS)
+        reinterpret_cast<uint4 *>(smem + C::OFF_IN)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
         for (int t = 0; t < TILES; ++t) { mbar_init(bar(B_ACC + t), 1); mbar_init(bar(B_ACT + t), 128); }
-        mbar_init(bar(B_CONST), 1);
         mbar_init(bar(B_IN), 128 * TILES);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(sbase + OFF_TMEM, 512);
+    if (warp == 1) tmem_alloc(sbase + C::OFF_TMEM, C::TMEM_COLS);
     fence_proxy_async();                 // zero-fills above must be visible to the tensor core's async proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + OFF_TMEM);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + C::OFF_TMEM);
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
+        // per unit the weight stream is: input conv (16 KiB + 4 KiB), 18 chunks per tower layer, heads (8 KiB)
         if (lane == 0) {
-            mbar_expect_tx(bar(B_CONST), WIN_BYTES + WHEAD_BYTES);
-            bulk_g2s(sbase + OFF_WIN, P.w_in, WIN_BYTES, bar(B_CONST));
-            bulk_g2s(sbase + OFF_WHEAD, P.w_heads, WHEAD_BYTES, bar(B_CONST));
             uint32_t it = 0;
+            auto push = [&](const uint8_t *src, uint32_t bytes) {
+                const int s = it % STAGES;
+                mbar_wait(bar(B_EMPTY + s), ((it / STAGES) & 1) ^ 1);
+                mbar_expect_tx(bar(B_FULL + s), bytes);
+                bulk_g2s(sbase + C::OFF_RING + s * STAGE_BYTES, src, bytes, bar(B_FULL + s));
+                ++it;
+            };
+            const uint8_t *tower = P.w_stream + WIN_BYTES;
+            const uint8_t *head_w = tower + (size_t)tower_layers * CHUNKS * STAGE_BYTES;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                const int nl = min(tower_layers, run_layers - 1);
-                for (int l = 0; l < nl; ++l) {
-                    const uint8_t *src = reinterpret_cast<const uint8_t *>(P.w_tower) + (size_t)l * CHUNKS * STAGE_BYTES;
-                    for (int c = 0; c < CHUNKS; ++c, ++it) {
-                        const int s = it % STAGES;
-                        mbar_wait(bar(B_EMPTY + s), ((it / STAGES) & 1) ^ 1);
-                        mbar_expect_tx(bar(B_FULL + s), STAGE_BYTES);
-                        bulk_g2s(sbase + OFF_RING + s * STAGE_BYTES, src + (size_t)c * STAGE_BYTES, STAGE_BYTES, bar(B_FULL + s));
-                    }
-                }
+                push(P.w_stream, WIN_CHUNK0);
+                push(P.w_stream + WIN_CHUNK0, WIN_BYTES - WIN_CHUNK0);
+                for (int c = 0; c < nl * CHUNKS; ++c) push(tower + (size_t)c * STAGE_BYTES, STAGE_BYTES);
+                if (heads) push(head_w, WHEAD_BYTES);
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
-            mbar_wait(bar(B_CONST), 0);
             uint32_t it = 0, in_phase = 0, act_phase = 0;
+            auto acquire = [&]() {               // wait for the next stage of the weight stream
+                const int s = it % STAGES;
+                mbar_wait(bar(B_FULL + s), (it / STAGES) & 1);
+                tc_fence_after();
+                return sbase + C::OFF_RING + s * STAGE_BYTES;
+            };
+            auto release = [&]() { umma_commit(bar(B_EMPTY + it % STAGES)); ++it; };
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
                 // ---- input conv: 9 taps x 8 (4 real) channels, two taps per K=16 step ----
                 mbar_wait(bar(B_IN), in_phase);
                 in_phase ^= 1;
                 tc_fence_after();
-                if (run_layers >= 1) {
+                for (int part = 0; part < 2; ++part) {
+                    const uint32_t b_rows = acquire();
                     for (int t = 0; t < TILES; ++t) {
-                        const uint32_t in_rows = sbase + OFF_IN + (MARGIN + t * TILE_M) * ROW_BYTES;
-                        for (int j = 0; j < 5; ++j) {
+                        const uint32_t in_rows = sbase + C::OFF_IN + (MARGIN + t * TILE_M) * ROW_BYTES;
+                        for (int j = part * 4; j < (part ? 5 : 4); ++j) {
                             const int tap0 = 2 * j, tap1 = 2 * j + 1;
-                            const int sh0 = (tap0 / 3 - 1) * 8 + (tap0 % 3 - 1);
-                            const uint32_t a0 = in_rows + sh0 * ROW_BYTES;
-                            uint32_t a1;
-                            if (tap1 < 9) a1 = in_rows + ((tap1 / 3 - 1) * 8 + (tap1 % 3 - 1)) * ROW_BYTES;
-                            else a1 = sbase + OFF_ZERO;
-                            const uint64_t ad = make_desc(a0, a1 - a0);
-                            const uint64_t bd = make_desc(sbase + OFF_WIN + j * 2 * W_LBO, W_LBO);
-                            umma(tmem_base + TM_ACC + t * 128, ad, bd, IDESC_128, j > 0);
+                            const uint32_t a0 = in_rows + ((tap0 / 3 - 1) * 8 + (tap0 % 3 - 1)) * ROW_BYTES;
+                            const uint32_t a1 = tap1 < 9 ? in_rows + ((tap1 / 3 - 1) * 8 + (tap1 % 3 - 1)) * ROW_BYTES : sbase + C::OFF_ZERO;
+                            umma(tmem_base + C::TM_ACC + t * 128, make_desc(a0, a1 - a0), make_desc(b_rows + (j - part * 4) * 2 * W_LBO, W_LBO),
+                                 IDESC_128, j > 0);
                         }
-                        umma_commit(bar(B_ACC + t));
+                        if (part) umma_commit(bar(B_ACC + t));
                     }
+                    release();
                 }
                 // ---- tower ----
-                const int nl = min(tower_layers, run_layers - 1);
                 for (int l = 0; l < nl; ++l) {
                     for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + t), act_phase);
                     act_phase ^= 1;
                     tc_fence_after();
-                    for (int c = 0; c < CHUNKS; ++c, ++it) {
-                        const int s = it % STAGES;
-                        mbar_wait(bar(B_FULL + s), (it / STAGES) & 1);
-                        tc_fence_after();
+                    for (int c = 0; c < CHUNKS; ++c) {
+                        const uint32_t b_rows = acquire();
                         const int half = c / 9, tap = c % 9;
                         const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
                         for (int t = 0; t < TILES; ++t) {
-                            const uint32_t a_rows = sbase + OFF_ACT + (MARGIN + t * TILE_M + shift) * ROW_BYTES + half * 8 * ACT_LBO;
-                            const uint32_t b_rows = sbase + OFF_RING + s * STAGE_BYTES;
+                            const uint32_t a_rows = sbase + C::OFF_ACT + (MARGIN + t * TILE_M + shift) * ROW_BYTES + half * 8 * C::ACT_LBO;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint64_t ad = make_desc(a_rows + 2 * j * ACT_LBO, ACT_LBO);
-                                const uint64_t bd = make_desc(b_rows + 2 * j * W_LBO, W_LBO);
-                                umma(tmem_base + TM_ACC + t * 128, ad, bd, IDESC_128, (c | j) != 0);
-                            }
+                            for (int j = 0; j < 4; ++j)
+                                umma(tmem_base + C::TM_ACC + t * 128, make_desc(a_rows + 2 * j * C::ACT_LBO, C::ACT_LBO),
+                                     make_desc(b_rows + 2 * j * W_LBO, W_LBO), IDESC_128, (c | j) != 0);
+                            if (c == CHUNKS - 1) umma_commit(bar(B_ACC + t));
                         }
-                        umma_commit(bar(B_EMPTY + s));
+                        release();
                     }
-                    for (int t = 0; t < TILES; ++t) umma_commit(bar(B_ACC + t));
                 }
                 // ---- heads: [128 rows x 128 ch] x [128 ch x 32] ----
                 for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + t), act_phase);
                 act_phase ^= 1;
                 tc_fence_after();
-                if (P.debug_layers < 0) {
+                if (heads) {
+                    const uint32_t b_rows = acquire();
                     for (int t = 0; t < TILES; ++t) {
-                        const uint32_t a_rows = sbase + OFF_ACT + (MARGIN + t * TILE_M) * ROW_BYTES;
+                        const uint32_t a_rows = sbase + C::OFF_ACT + (MARGIN + t * TILE_M) * ROW_BYTES;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const uint64_t ad = make_desc(a_rows + 2 * j * ACT_LBO, ACT_LBO);
-                            const uint64_t bd = make_desc(sbase + OFF_WHEAD + 2 * j * HEAD_LBO, HEAD_LBO);
-                            umma(tmem_base + TM_ACC + t * 128, ad, bd, IDESC_HEAD, j > 0);
-                        }
+                        for (int j = 0; j < 8; ++j)
+                            umma(tmem_base + C::TM_ACC + t * 128, make_desc(a_rows + 2 * j * C::ACT_LBO, C::ACT_LBO),
+                                 make_desc(b_rows + 2 * j * HEAD_LBO, HEAD_LBO), IDESC_HEAD, j > 0);
                         umma_commit(bar(B_ACC + t));
                     }
+                    release();
                 }
-                // the next unit's input planes may only be consumed after its epilogue threads re-stage them,
-                // which they do after finishing this unit (B_IN handshake above).
             }
         }
     } else {
@@ -346,14 +351,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
         const int gtid = (warp - 2 - tile * 4) * 32 + lane;   // 0..127 within the tile's epilogue group
         int bit, cell;
         const bool real = row_is_real(r, bit, cell);
-        float *shift_base = reinterpret_cast<float *>(smem + OFF_SHIFT) + tile * 2 * F;
-        float *vpart = reinterpret_cast<float *>(smem + OFF_VPART) + tile * 4;
+        float *shift_base = reinterpret_cast<float *>(smem + C::OFF_SHIFT) + tile * 2 * F;
+        float *vpart = reinterpret_cast<float *>(smem + C::OFF_VPART) + tile * 4;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        uint8_t *act_row = smem + OFF_ACT + (MARGIN + tile * TILE_M + r) * ROW_BYTES;
+        uint8_t *act_row = smem + C::OFF_ACT + (MARGIN + tile * TILE_M + r) * ROW_BYTES;
         uint32_t acc_phase = 0;
 
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-            const int board = unit * UNIT_BOARDS + tile * 2 + bit;
+            const int board = unit * C::UNIT_BOARDS + tile * 2 + bit;
             const bool live = real && board < n_boards;
             // ---- stage the input planes of this row: 4 feature channels + 4 zeros, bf16 ----
             {
@@ -371,7 +376,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
                     v.x = pack_bf16(f[0], f[1]);
                     v.y = pack_bf16(f[2], f[3]);
                 }
-                *reinterpret_cast<uint4 *>(smem + OFF_IN + (MARGIN + tile * TILE_M + r) * ROW_BYTES) = v;
+                *reinterpret_cast<uint4 *>(smem + C::OFF_IN + (MARGIN + tile * TILE_M + r) * ROW_BYTES) = v;
                 fence_proxy_async();
                 mbar_arrive(bar(B_IN));
             }
@@ -388,9 +393,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
 #pragma unroll 1
                 for (int q = 0; q < 4; ++q) {          // 32 channels at a time
                     uint32_t a[32];
-                    tmem_ld32(lane_addr + TM_ACC + tile * 128 + q * 32, a);
+                    tmem_ld32(lane_addr + C::TM_ACC + tile * 128 + q * 32, a);
                     uint32_t res[32];
-                    if (second) tmem_ld32(lane_addr + TM_RES + tile * 128 + q * 32, res);
+                    if (second) tmem_ld32(lane_addr + C::TM_RES + tile * 128 + q * 32, res);
                     tmem_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -399,7 +404,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
                         v = live ? fmaxf(v, 0.f) : 0.f;
                         a[i] = __float_as_uint(v);
                     }
-                    if (writes_res) tmem_st32(lane_addr + TM_RES + tile * 128 + q * 32, a);
+                    if (writes_res) tmem_st32(lane_addr + C::TM_RES + tile * 128 + q * 32, a);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 o;
@@ -407,7 +412,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
                         o.y = pack_bf16(__uint_as_float(a[8 * g + 2]), __uint_as_float(a[8 * g + 3]));
                         o.z = pack_bf16(__uint_as_float(a[8 * g + 4]), __uint_as_float(a[8 * g + 5]));
                         o.w = pack_bf16(__uint_as_float(a[8 * g + 6]), __uint_as_float(a[8 * g + 7]));
-                        *reinterpret_cast<uint4 *>(act_row + (q * 4 + g) * ACT_LBO) = o;
+                        *reinterpret_cast<uint4 *>(act_row + (q * 4 + g) * C::ACT_LBO) = o;
                     }
                     if (P.debug_layers >= 0 && l == run_layers - 1 && live) {
                         float *dst = P.debug_act + ((size_t)board * 49 + cell) * F + q * 32;
@@ -419,13 +424,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
                 tc_fence_before();
                 mbar_arrive(bar(B_ACT + tile));
             }
-            if (P.debug_layers < 0) {
-                // ---- heads ----
+            if (heads) {
                 mbar_wait(bar(B_ACC + tile), acc_phase);
                 acc_phase ^= 1;
                 tc_fence_after();
                 uint32_t a[32];
-                tmem_ld32(lane_addr + TM_ACC + tile * 128, a);
+                tmem_ld32(lane_addr + C::TM_ACC + tile * 128, a);
                 tmem_wait_ld();
                 float vterm = 0.f;
                 if (live) {
@@ -441,18 +445,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
                 tc_fence_before();
                 group_sync(tile);
                 if (gtid < 2) {
-                    const int b = unit * UNIT_BOARDS + tile * 2 + gtid;
+                    const int b = unit * C::UNIT_BOARDS + tile * 2 + gtid;
                     if (b < n_boards) P.values[b] = tanhf(vpart[2 * gtid] + vpart[2 * gtid + 1] + __ldg(P.fc_b));
                 }
                 group_sync(tile);
-                // accumulator columns are free again for the next unit's input conv: the MMA warp waits on B_IN,
-                // which this thread arrives on only after the loads above completed.
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 }  // namespace
@@ -461,81 +463,105 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_net_tc(const TcParams P)
 // host side
 // ------------------------------------------------------------------------------------------
 
-static __nv_bfloat16 to_bf16(float v) { return __float2bfloat16_rn(v); }
-
-int az_net_tc_prepare(az_context *ctx, AzNet *net, const std::vector<float> &h)
+namespace {
+// Re-tile the fp32 TF-layout parameters into the UMMA operand images the kernel streams, folding the
+// batch-norm scale 1/sqrt(var+eps) of the conv's own BN layer into its output channels.
+__global__ void k_tile_tower(const float *__restrict__ w_tower, const float *__restrict__ scale, int tower_layers,
+                             __nv_bfloat16 *__restrict__ out)
 {
-    (void)ctx;
-    const int f = net->filters, blocks = net->blocks, layers = net->layers;
-    const size_t n_in = 9 * 4 * (size_t)f, n_tower = (size_t)2 * blocks * 9 * f * f;
-    const float *w_in = h.data();
-    const float *w_tower = w_in + n_in;
-    const float *w_policy = w_tower + n_tower;
-    const float *w_value = w_policy + (size_t)f * 17;
-    const float *bn = w_value + f + 49 + 1;
-    std::vector<float> scale((size_t)layers * f), shift((size_t)layers * f);
-    for (int l = 0; l < layers; ++l)
-        for (int c = 0; c < f; ++c) {
-            const double s = 1.0 / std::sqrt((double)bn[(size_t)(2 * l + 1) * f + c] + (double)AZ_BN_EPS);
-            scale[(size_t)l * f + c] = (float)s;
-            shift[(size_t)l * f + c] = (float)(-(double)bn[(size_t)(2 * l) * f + c] * s);
-        }
-    // tower: [layer][chunk = half*9 + tap][kg 0..7][cout][i 0..7]
-    std::vector<__nv_bfloat16> tw((size_t)2 * blocks * CHUNKS * 8 * f * 8);
-    for (int l = 0; l < 2 * blocks; ++l)
-        for (int c = 0; c < CHUNKS; ++c) {
-            const int half = c / 9, tap = c % 9;
-            for (int kg = 0; kg < 8; ++kg)
-                for (int co = 0; co < f; ++co)
-                    for (int i = 0; i < 8; ++i) {
-                        const int cin = half * 64 + kg * 8 + i;
-                        const float w = w_tower[(((size_t)l * 9 + tap) * f + cin) * f + co] * scale[(size_t)(l + 1) * f + co];
-                        tw[((((size_t)l * CHUNKS + c) * 8 + kg) * f + co) * 8 + i] = to_bf16(w);
-                    }
-        }
-    // input conv: [kstep j][g][cout][i]: tap = 2j+g (tap 9 = zero), channels 0..3 real
-    std::vector<__nv_bfloat16> wi((size_t)5 * 2 * f * 8);
-    for (int j = 0; j < 5; ++j)
-        for (int g = 0; g < 2; ++g)
-            for (int co = 0; co < f; ++co)
-                for (int i = 0; i < 8; ++i) {
-                    const int tap = 2 * j + g;
-                    float w = 0.f;
-                    if (tap < 9 && i < 4) w = w_in[((size_t)tap * 4 + i) * f + co] * scale[co];
-                    wi[(((size_t)j * 2 + g) * f + co) * 8 + i] = to_bf16(w);
-                }
-    // heads: [kg][row 0..31][i]: rows 0..16 policy planes, row 17 value plane
-    std::vector<__nv_bfloat16> wh((size_t)KG * HEAD_N * 8);
-    for (int kg = 0; kg < KG; ++kg)
-        for (int row = 0; row < HEAD_N; ++row)
-            for (int i = 0; i < 8; ++i) {
-                const int cin = kg * 8 + i;
-                float w = 0.f;
-                if (row < 17) w = w_policy[(size_t)cin * 17 + row];
-                else if (row == 17) w = w_value[cin];
-                wh[((size_t)kg * HEAD_N + row) * 8 + i] = to_bf16(w);
-            }
-    AZ_CUDA(cudaMalloc(&net->tc_w, tw.size() * 2));
-    AZ_CUDA(cudaMemcpy(net->tc_w, tw.data(), tw.size() * 2, cudaMemcpyHostToDevice));
-    AZ_CUDA(cudaMalloc(&net->tc_w_in, wi.size() * 2));
-    AZ_CUDA(cudaMemcpy(net->tc_w_in, wi.data(), wi.size() * 2, cudaMemcpyHostToDevice));
-    AZ_CUDA(cudaMalloc(&net->tc_w_heads, wh.size() * 2));
-    AZ_CUDA(cudaMemcpy(net->tc_w_heads, wh.data(), wh.size() * 2, cudaMemcpyHostToDevice));
-    AZ_CUDA(cudaMalloc(&net->tc_shift, shift.size() * 4));
-    AZ_CUDA(cudaMemcpy(net->tc_shift, shift.data(), shift.size() * 4, cudaMemcpyHostToDevice));
-    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<AZ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<AZ_IN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    // out index: ((((l*18 + chunk)*8 + kg)*128 + co)*8 + i)
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)tower_layers * CHUNKS * 8 * F * 8;
+    if (idx >= total) return;
+    const int i = (int)(idx & 7);
+    const int co = (int)((idx >> 3) & 127);
+    const int kg = (int)((idx >> 10) & 7);
+    const int chunk = (int)((idx >> 13) % CHUNKS);
+    const int l = (int)((idx >> 13) / CHUNKS);
+    const int half = chunk / 9, tap = chunk % 9;
+    const int cin = half * 64 + kg * 8 + i;
+    const float w = w_tower[(((size_t)l * 9 + tap) * F + cin) * F + co] * scale[(size_t)(l + 1) * F + co];
+    out[idx] = __float2bfloat16_rn(w);
+}
+
+__global__ void k_tile_small(const float *__restrict__ w_in, const float *__restrict__ w_policy, const float *__restrict__ w_value,
+                             const float *__restrict__ bn_raw, const float *__restrict__ scale, int layers,
+                             __nv_bfloat16 *__restrict__ out_in, __nv_bfloat16 *__restrict__ out_heads, float *__restrict__ shift)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 5 * 2 * F * 8) {                   // input conv: [kstep j][g][cout][i], tap = 2j+g (tap 9 = zero), 4 real channels
+        const int i = idx & 7, co = (idx >> 3) & 127, g = (idx >> 10) & 1, j = idx >> 11;
+        const int tap = 2 * j + g;
+        float w = 0.f;
+        if (tap < 9 && i < 4) w = w_in[((size_t)tap * 4 + i) * F + co] * scale[co];
+        out_in[idx] = __float2bfloat16_rn(w);
+    }
+    if (idx < KG * HEAD_N * 8) {                 // heads: [kg][row 0..31][i]: rows 0..16 policy planes, row 17 value plane
+        const int i = idx & 7, row = (idx >> 3) & 31, kg = idx >> 8;
+        const int cin = kg * 8 + i;
+        float w = 0.f;
+        if (row < 17) w = w_policy[(size_t)cin * 17 + row];
+        else if (row == 17) w = w_value[cin];
+        out_heads[idx] = __float2bfloat16_rn(w);
+    }
+    if (idx < layers * F) {                      // epilogue shift = -mean * scale, in double like the reference's BN
+        const int l = idx / F, c = idx % F;
+        const double sc = 1.0 / sqrt((double)bn_raw[(size_t)(2 * l + 1) * F + c] + (double)AZ_BN_EPS);
+        shift[idx] = (float)(-(double)bn_raw[(size_t)(2 * l) * F + c] * sc);
+    }
+}
+}  // namespace
+
+int az_net_tc_alloc(AzNet *net)
+{
+    // one contiguous weight stream: [input conv][tower][heads], exactly the order the producer walks
+    const size_t tower = (size_t)2 * net->blocks * CHUNKS * STAGE_BYTES;
+    AZ_CUDA(cudaMalloc(&net->tc_stream, WIN_BYTES + tower + WHEAD_BYTES));
+    net->tc_w_in = reinterpret_cast<__nv_bfloat16 *>(net->tc_stream);
+    net->tc_w = reinterpret_cast<__nv_bfloat16 *>(net->tc_stream + WIN_BYTES);
+    net->tc_w_heads = reinterpret_cast<__nv_bfloat16 *>(net->tc_stream + WIN_BYTES + tower);
+    AZ_CUDA(cudaMalloc(&net->tc_shift, (size_t)net->layers * F * 4));
+    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<1, AZ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<1, AZ_IN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<2, AZ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<2, AZ_IN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+    const char *env = getenv("AZ_NET_TILES");          // tuning knob: 1 = two single-tile CTAs per SM, 2 = one two-tile CTA per SM
+    net->tc_tiles = (env && atoi(env) == 2) ? 2 : (env && atoi(env) == 1) ? 1 : AZ_NET_TILES_DEFAULT;
+    return AZ_OK;
+}
+
+int az_net_tc_prepare(az_context *ctx, AzNet *net)
+{
+    cudaStream_t s = ctx->stream;
+    const size_t tower = (size_t)2 * net->blocks * CHUNKS * 8 * F * 8;
+    k_tile_tower<<<(unsigned)((tower + 255) / 256), 256, 0, s>>>(net->w_tower, net->bn_scale, 2 * net->blocks, net->tc_w);
+    const int small = std::max(std::max(5 * 2 * F * 8, KG * HEAD_N * 8), net->layers * F);
+    k_tile_small<<<(small + 255) / 256, 256, 0, s>>>(net->w_in, net->w_policy, net->w_value, net->bn_raw, net->bn_scale, net->layers,
+                                                     net->tc_w_in, net->tc_w_heads, net->tc_shift);
+    AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
 
 void az_net_tc_release(AzNet *net)
 {
-    if (net->tc_w) cudaFree(net->tc_w);
-    if (net->tc_w_in) cudaFree(net->tc_w_in);
-    if (net->tc_w_heads) cudaFree(net->tc_w_heads);
+    if (net->tc_stream) cudaFree(net->tc_stream);
     if (net->tc_shift) cudaFree(net->tc_shift);
+    net->tc_stream = nullptr;
     net->tc_w = net->tc_w_in = net->tc_w_heads = nullptr;
     net->tc_shift = nullptr;
+}
+
+template <int TILES>
+static void tc_launch_variant(az_context *ctx, const TcParams &P, int in_kind, int n)
+{
+    using C = Cfg<TILES>;
+    const int units = (n + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS;
+    const int slots = ctx->sm_count * C::CTAS_PER_SM;
+    const int grid = units < slots ? units : slots;
+    if (in_kind == AZ_IN_F32)
+        k_net_tc<TILES, AZ_IN_F32><<<grid, C::NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(P);
+    else
+        k_net_tc<TILES, AZ_IN_POS><<<grid, C::NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(P);
 }
 
 static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
@@ -547,21 +573,15 @@ static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind,
     P.n_ptr = d_count;
     P.layers = net->layers;
     P.debug_layers = debug_layers;
-    P.w_tower = net->tc_w;
-    P.w_in = net->tc_w_in;
-    P.w_heads = net->tc_w_heads;
+    P.w_stream = net->tc_stream;
     P.shift = net->tc_shift;
     P.fc_w = net->fc_w;
     P.fc_b = net->fc_b;
     P.logits = d_logits;
     P.values = d_values;
     P.debug_act = d_debug;
-    const int units = (n + UNIT_BOARDS - 1) / UNIT_BOARDS;
-    const int grid = units < ctx->sm_count ? units : ctx->sm_count;
-    if (in_kind == AZ_IN_F32)
-        k_net_tc<AZ_IN_F32><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(P);
-    else
-        k_net_tc<AZ_IN_POS><<<grid, NUM_THREADS, SMEM_BYTES, ctx->stream>>>(P);
+    if (net->tc_tiles == 1) tc_launch_variant<1>(ctx, P, in_kind, n);
+    else tc_launch_variant<2>(ctx, P, in_kind, n);
     ctx->launches++;
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
