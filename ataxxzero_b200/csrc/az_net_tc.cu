@@ -146,6 +146,34 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
         "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, with the 64-bit descriptors assembled from a running low word (start address field) and a constant high word:
+// stepping through taps / k-groups / stages is then ONE integer add per operand on the issuing thread
+__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -276,7 +304,7 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0, in_phase = 0, act_phase = 0;
             auto acquire = [&]() {               // wait for the next stage of the weight stream
                 const int s = it % STAGES;
@@ -306,23 +334,36 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                     release();
                 }
                 // ---- tower ----
+                // descriptor words: [0,14) start address >> 4, [16,30) LBO >> 4 | hi word: SBO >> 4, version
+                const uint32_t a_hi = (uint32_t)(make_desc(0, C::ACT_LBO) >> 32), b_hi = (uint32_t)(make_desc(0, W_LBO) >> 32);
+                const uint32_t a_lo0 = (uint32_t)make_desc(sbase + C::OFF_ACT + MARGIN * ROW_BYTES, C::ACT_LBO);
+                const uint32_t b_lo0 = (uint32_t)make_desc(sbase + C::OFF_RING, W_LBO);
+                constexpr uint32_t A_KSTEP = (2 * C::ACT_LBO) >> 4, B_KSTEP = (2 * W_LBO) >> 4, A_HALF = (8 * C::ACT_LBO) >> 4;
                 for (int l = 0; l < nl; ++l) {
                     for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + t), act_phase);
                     act_phase ^= 1;
                     tc_fence_after();
-                    for (int c = 0; c < CHUNKS; ++c) {
-                        const uint32_t b_rows = acquire();
-                        const int half = c / 9, tap = c % 9;
-                        const int shift = (tap / 3 - 1) * 8 + (tap % 3 - 1);
-                        for (int t = 0; t < TILES; ++t) {
-                            const uint32_t a_rows = sbase + C::OFF_ACT + (MARGIN + t * TILE_M + shift) * ROW_BYTES + half * 8 * C::ACT_LBO;
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                umma(tmem_base + C::TM_ACC + t * 128, make_desc(a_rows + 2 * j * C::ACT_LBO, C::ACT_LBO),
-                                     make_desc(b_rows + 2 * j * W_LBO, W_LBO), IDESC_128, (c | j) != 0);
-                            if (c == CHUNKS - 1) umma_commit(bar(B_ACC + t));
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int s = it % STAGES;
+                            mbar_wait(bar(B_FULL + s), (it / STAGES) & 1);
+                            tc_fence_after();
+                            const uint32_t b_lo = b_lo0 + s * (STAGE_BYTES >> 4);
+                            // tap shift in rows == shift in 16-byte units of the start-address field
+                            const uint32_t a_lo = a_lo0 + half * A_HALF + (uint32_t)((tap / 3 - 1) * 8 + (tap % 3 - 1));
+#pragma unroll
+                            for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    umma_lo(tmem_base + C::TM_ACC + t * 128, a_lo + t * TILE_M + j * A_KSTEP, a_hi, b_lo + j * B_KSTEP, b_hi,
+                                            IDESC_128, (half | tap | j) != 0);
+                                if (half == 1 && tap == 8) umma_commit(bar(B_ACC + t));
+                            }
+                            umma_commit(bar(B_EMPTY + s));
+                            ++it;
                         }
-                        release();
                     }
                 }
                 // ---- heads: [128 rows x 128 ch] x [128 ch x 32] ----

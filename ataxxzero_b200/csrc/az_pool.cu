@@ -19,6 +19,7 @@ using namespace aztree;
 void aztree_launch_tick(const PoolDev &P, cudaStream_t s);
 void aztree_launch_init_all(const PoolDev &P, const az_position &pos, cudaStream_t s);
 void aztree_launch_set_root(const PoolDev &P, int g, const az_position &pos, cudaStream_t s);
+void aztree_launch_set_roots(const PoolDev &P, const az_position *d_pos, cudaStream_t s);
 void aztree_launch_play(const PoolDev &P, int g, int move, int *d_status, cudaStream_t s);
 void aztree_launch_release(const PoolDev &P, const DoneEntry *d_done, int n, cudaStream_t s);
 void aztree_launch_features(const az_position *d_pos, int n, float *d_out, cudaStream_t s);
@@ -32,7 +33,7 @@ struct az_pool {
     float *d_features = nullptr;          // external mode: [G][196]
     DoneEntry *d_done_snapshot = nullptr; // copy of the done queue being drained
     // pinned host mirrors
-    int32_t *h_counts = nullptr;          // [0] req_count, [1] done_count, [2] status
+    int32_t *h_counts = nullptr;          // [0] req_count, [1] busy_count, [2] status, [3] done_count
     DoneEntry *h_done = nullptr;          // [2G]
     uint32_t *h_record = nullptr;         // one record buffer
     std::vector<Game> h_games;
@@ -69,7 +70,8 @@ int check_game_errors(az_pool *pool)
 int launch_tree(az_pool *pool, bool consume = true)
 {
     cudaStream_t s = pool->ctx->stream;
-    if (consume) AZ_CUDA(cudaMemsetAsync(pool->dev.req_count, 0, sizeof(int32_t), s));
+    if (consume) AZ_CUDA(cudaMemsetAsync(pool->dev.req_count, 0, 2 * sizeof(int32_t), s));
+    else AZ_CUDA(cudaMemsetAsync(pool->dev.req_count + 1, 0, sizeof(int32_t), s));
     pool->dev.consume = consume ? 1 : 0;
     aztree_launch_tick(pool->dev, s);
     pool->ticks++;
@@ -143,9 +145,9 @@ std::string record_to_json(const uint32_t *rec, int words, int plies, int result
 int drain_finished(az_pool *pool, FILE *out, int64_t *games_written, bool copy_payload = true)
 {
     cudaStream_t s = pool->ctx->stream;
-    AZ_CUDA(cudaMemcpyAsync(pool->h_counts + 1, pool->dev.done_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(pool->h_counts + 3, pool->dev.done_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
-    const int n = pool->h_counts[1];
+    const int n = pool->h_counts[3];
     if (n == 0) return AZ_OK;
     AZ_CUDA(cudaMemcpyAsync(pool->h_done, pool->dev.done, sizeof(DoneEntry) * n, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaMemcpyAsync(pool->d_done_snapshot, pool->dev.done, sizeof(DoneEntry) * n, cudaMemcpyDeviceToDevice, s));
@@ -197,7 +199,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
     pool->cfg = *cfg;
     if (pool->cfg.max_plies <= 0) pool->cfg.max_plies = 400;
     if (pool->cfg.node_capacity <= 0) pool->cfg.node_capacity = cfg->visits + 64;
-    if (pool->cfg.steps_per_tick <= 0) pool->cfg.steps_per_tick = 16;
+    if (pool->cfg.steps_per_tick <= 0) pool->cfg.steps_per_tick = 8;
     AZ_REQUIRE(pool->cfg.node_capacity < (1 << 24), AZ_ERR_ARG, "az_pool_create: node_capacity too large");
     PoolDev &D = pool->dev;
     D.G = cfg->games;
@@ -207,6 +209,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
     D.noise = cfg->noise ? 1 : 0;
     D.auto_play = cfg->auto_play ? 1 : 0;
     D.steps_per_tick = pool->cfg.steps_per_tick;
+    D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : 48;
     D.seed = cfg->seed;
     D.rec_cap_words = cfg->auto_play ? (uint32_t)pool->cfg.max_plies * kRecWordsPerPly : 16;
     const size_t G = (size_t)D.G;
@@ -225,7 +228,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
     rc |= dev_alloc(&D.gstack, G * D.C, false);
     rc |= dev_alloc(&D.req_pos, G);
     rc |= dev_alloc(&D.req_game, G);
-    rc |= dev_alloc(&D.req_count, 1);
+    rc |= dev_alloc(&D.req_count, 2);
     rc |= dev_alloc(&D.logits, G * AZ_LOGITS);
     rc |= dev_alloc(&D.values, G);
     rc |= dev_alloc(&D.records, G * 2 * D.rec_cap_words, false);
@@ -306,6 +309,26 @@ extern "C" int az_pool_set_root(az_pool *pool, int game, const az_position *root
     return AZ_OK;
 }
 
+extern "C" int az_pool_set_roots(az_pool *pool, const az_position *roots)
+{
+    AZ_REQUIRE(pool && roots, AZ_ERR_ARG, "az_pool_set_roots: null argument");
+    AZ_REQUIRE(pool->pending_requests == 0, AZ_ERR_STATE, "az_pool_set_roots: evaluations are outstanding (az_pool_provide first)");
+    for (int g = 0; g < pool->dev.G; ++g) {
+        const az_position &r = roots[g];
+        const uint64_t all = r.pieces[0] | r.pieces[1] | r.blockers;
+        AZ_REQUIRE(!(r.pieces[0] & r.pieces[1]) && !((r.pieces[0] | r.pieces[1]) & r.blockers) && !(all >> 49) &&
+                       (r.pieces[0] | r.pieces[1]),
+                   AZ_ERR_ARG, "az_pool_set_roots: invalid position for game %d", g);
+    }
+    cudaStream_t s = pool->ctx->stream;
+    AZ_CUDA(cudaMemcpyAsync(pool->dev.req_pos, roots, sizeof(az_position) * pool->dev.G, cudaMemcpyHostToDevice, s));
+    aztree_launch_set_roots(pool->dev, pool->dev.req_pos, s);     // req_pos is free between ticks: reuse it as staging
+    pool->launches++;
+    AZ_CUDA(cudaStreamSynchronize(s));
+    AZ_CUDA(cudaGetLastError());
+    return check_game_errors(pool);
+}
+
 extern "C" int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out)
 {
     AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_run: null pool");
@@ -315,10 +338,10 @@ extern "C" int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out)
     for (int t = 0; t < max_ticks; ++t) {
         int rc = launch_tree(pool);
         if (rc) return rc;
-        AZ_CUDA(cudaMemcpyAsync(pool->h_counts, pool->dev.req_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaMemcpyAsync(pool->h_counts, pool->dev.req_count, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         if ((rc = launch_net(pool))) return rc;
         AZ_CUDA(cudaStreamSynchronize(s));
-        if (pool->h_counts[0] == 0) {           // nobody asked for an evaluation: every tree is done (or stalled)
+        if (pool->h_counts[0] == 0 && pool->h_counts[1] == 0) {   // no requests, nobody mid-step: every tree is done (or stalled)
             if (idle_out) *idle_out = 1;
             break;
         }
@@ -344,7 +367,7 @@ extern "C" int az_pool_collect(az_pool *pool, float *features, int32_t *n_reques
         AZ_CUDA(cudaStreamSynchronize(s));
         if ((rc = check_game_errors(pool))) return rc;
         bool busy = false;
-        for (int g = 0; g < pool->dev.G; ++g) busy |= pool->h_games[g].status == ST_IDLE;
+        for (int g = 0; g < pool->dev.G; ++g) busy |= pool->h_games[g].status == ST_IDLE || pool->h_games[g].status == ST_DESCEND;
         if (!busy) break;                       // every tree is waiting, done or stalled
     }
     const int n = pool->h_counts[0];

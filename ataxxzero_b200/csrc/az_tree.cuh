@@ -3,15 +3,17 @@
 //
 // One tree per game, one fixed-stride slot per node (no allocator metadata on the hot path):
 //
-//   node slot (7168 B, 128-B aligned):
+//   node slot (9216 B, 128-B aligned):
 //     [   0,   64)  header: position, value, child count L, visit count N, flags
 //     [  64, 2112)  P[256]      f64  prior                      (self_play_client.cpp:151 posterior)
 //     [2112, 4160)  W[256]      f64  edge_total_score           (:283)
-//     [4160, 5184)  n[256]      u32  edge_visits                (:282; integral, so exact as u32)
-//     [5184, 6208)  child[256]  i32  child node index, -1 = no edge yet (:281)
-//     [6208, 6720)  move[256]   u16  from | to<<8, reference movegen order (cpp/movegen.cpp:16-66)
-//     [6720, 6976)  rank[256]   u8   position of the move in the reference's hash-map iteration order
-//                                    (select_action's `>=` tie-break walks that order, :345-358)
+//     [4160, 6208)  Q[256]      f64  W/n, refreshed by backup   (:288-292 get_edge_score; select never divides W)
+//     [6208, 7232)  n[256]      u32  edge_visits                (:282; integral, so exact as u32)
+//     [7232, 8256)  child[256]  i32  child node index, -1 = no edge yet (:281)
+//     [8256, 8768)  move[256]   u16  from | to<<8, reference movegen order (cpp/movegen.cpp:16-66)
+//     [8768, 9024)  rank[256]   u8   position of the move in the reference's hash-map iteration order
+//                                    (select_action's `>=` tie-break walks that order, :345-358); filled in
+//                                    lazily, the first time a node actually sees an exact tie at its maximum
 //   Children of a node are a struct-of-arrays inside its slot, so a warp reads P/W/n of 32 children
 //   with three coalesced loads.  L < 256 is the reference's own bound (movegen.cpp:69).
 //
@@ -23,13 +25,18 @@
 
 namespace aztree {
 
-constexpr int kNodeStride = 7168;
-constexpr int kOffP = 64, kOffW = 2112, kOffN = 4160, kOffChild = 5184, kOffMove = 6208, kOffRank = 6720;
+constexpr int kNodeStride = 9216;
+constexpr int kOffP = 64, kOffW = 2112, kOffQ = 4160, kOffN = 6208, kOffChild = 7232, kOffMove = 8256, kOffRank = 8768;
 constexpr int kMaxPath = 1024;
 constexpr int kRecWordsPerPly = 6 + 2 * 256;    // worst-case record words per ply
 
-enum : uint32_t { NF_TERMINAL = 1u, NF_POPULATED = 2u };
-enum : int32_t { ST_IDLE = 0, ST_WAIT = 1, ST_DONE = 2, ST_STALL = 3, ST_ERROR = 4 };
+enum : uint32_t {
+    NF_TERMINAL = 1u,
+    NF_POPULATED = 2u,
+    NF_RANKED = 4u,      // rank[] is valid for the node's current population
+    NF_REPOPULATED = 8u  // the node became a root: the reference re-inserted its posterior into a clear()ed map (:489-490)
+};
+enum : int32_t { ST_IDLE = 0, ST_WAIT = 1, ST_DONE = 2, ST_STALL = 3, ST_ERROR = 4, ST_DESCEND = 5 };
 enum : int32_t { ERR_NODES = 1, ERR_PATH = 2, ERR_MOVES = 3 };
 
 struct __align__(16) NodeHdr {
@@ -39,7 +46,7 @@ struct __align__(16) NodeHdr {
     int32_t N;               // all_edge_visits
     int32_t turn;            // absolute side to move: 0 = x, 1 = o
     uint32_t flags;
-    int32_t buckets;         // bucket count of the reference's posterior map after population
+    int32_t reserved;
     int32_t pad[5];
 };
 static_assert(sizeof(NodeHdr) == 64, "node header is 64 bytes");
@@ -78,13 +85,14 @@ struct PoolDev {
     uint32_t *gstack;        // [G][C]
     az_position *req_pos;    // [G]
     int32_t *req_game;       // [G]
-    int32_t *req_count;      // [1]
+    int32_t *req_count;      // [2]: [0] requests of this tick, [1] games that still have work but made no request
     float *logits;           // [G][833]
     float *values;           // [G]
     uint32_t *records;       // [G][2][rec_cap_words]
     DoneEntry *done;         // [2G]
     int32_t *done_count;     // [1]
     int32_t G, C, visits, max_plies, noise, auto_play, steps_per_tick;
+    int32_t levels_per_tick; // bound on tree levels a game may descend per tick (tail latency of deep endgame lines)
     int32_t consume;         // 1: evaluations of the previous requests are in logits/values; 0: top-up tick, leave waiting games alone
     uint32_t rec_cap_words;
     uint64_t seed;

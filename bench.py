@@ -290,9 +290,7 @@ def run_ours(args):
     packed = network.packed()
     net.load_weights(ctx, network)
     pool = search.Pool(ctx, games, visits, eval_mode=search.EVAL_BF16, noise=True, auto_play=True, seed=1000 + rank)
-    roots = rules.array_to_positions(synthetic_roots(ctx, games, seed=rank))
-    for g, p in enumerate(roots):
-        pool.set_root(g, p)
+    pool.set_roots(synthetic_roots(ctx, games, seed=rank))
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
     for _ in range(w):

@@ -132,7 +132,7 @@ typedef struct {
                                0: search only (MCTS::step / MCTS::play driven by the caller)                 */
     int32_t eval_mode;      /* AZ_NET_FP32, AZ_NET_BF16 or AZ_EVAL_EXTERNAL                                   */
     int32_t node_capacity;  /* nodes per tree; 0 = visits + 64                                               */
-    int32_t steps_per_tick; /* max MCTS steps a game may take per tick without needing the net; 0 = 16      */
+    int32_t steps_per_tick; /* max MCTS steps a game may take per tick without needing the net; 0 = 8       */
     uint64_t seed;          /* Philox stream for move sampling and Dirichlet noise                           */
     char start_fen[64];     /* "" = STARTING_GAME_POSITION (self_play_client.cpp:23)                         */
 } az_pool_config;
@@ -158,6 +158,8 @@ int az_pool_stats_get(az_pool *pool, az_pool_stats *out);
 
 /* MCTS(thread_id, board, use_dirichlet_noise) ctor (self_play_client.cpp:375-384): reset tree `game` to `root` */
 int az_pool_set_root(az_pool *pool, int game, const az_position *root);
+/* the same for every tree at once: roots is az_position[cfg.games] (host memory) */
+int az_pool_set_roots(az_pool *pool, const az_position *roots);
 /* Advance every tree with the internal net until each has root visits >= cfg.visits (search mode) or
  * `max_ticks` ticks have run.  *idle_out = 1 when no tree needs more work. */
 int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out);

@@ -10,7 +10,6 @@ T = int(sys.argv[3]) if len(sys.argv) > 3 else 96
 ctx = az.Context(0)
 net.load_weights(ctx, model.Network.random_init(seed=0))
 pool = search.Pool(ctx, G, V, eval_mode=search.EVAL_BF16, noise=True, auto_play=True, seed=1)
-for g, p in enumerate(rules.array_to_positions(bench.synthetic_roots(ctx, G, 0))):
-    pool.set_root(g, p)
+pool.set_roots(bench.synthetic_roots(ctx, G, 0))
 pool.selfplay_ticks(T)
 print("ok", pool.stats())
