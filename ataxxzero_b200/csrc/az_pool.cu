@@ -70,8 +70,12 @@ int check_game_errors(az_pool *pool)
 int launch_tree(az_pool *pool, bool consume = true)
 {
     cudaStream_t s = pool->ctx->stream;
-    if (consume) AZ_CUDA(cudaMemsetAsync(pool->dev.req_count, 0, 2 * sizeof(int32_t), s));
-    else AZ_CUDA(cudaMemsetAsync(pool->dev.req_count + 1, 0, sizeof(int32_t), s));
+    if (consume) {
+        AZ_CUDA(cudaMemcpyAsync(pool->dev.req_count + 2, pool->dev.req_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        AZ_CUDA(cudaMemsetAsync(pool->dev.req_count, 0, 2 * sizeof(int32_t), s));
+    } else {
+        AZ_CUDA(cudaMemsetAsync(pool->dev.req_count + 1, 0, sizeof(int32_t), s));
+    }
     pool->dev.consume = consume ? 1 : 0;
     aztree_launch_tick(pool->dev, s);
     pool->ticks++;
@@ -83,7 +87,7 @@ int launch_tree(az_pool *pool, bool consume = true)
 
 int launch_net(az_pool *pool)
 {
-    int rc = az_net_forward_internal(pool->ctx, pool->dev.req_pos, AZ_IN_POS, pool->dev.G, pool->cfg.eval_mode, pool->dev.logits,
+    int rc = az_net_forward_internal(pool->ctx, pool->dev.req_pos, AZ_IN_POS, pool->dev.cap, pool->cfg.eval_mode, pool->dev.logits,
                                      pool->dev.values, pool->dev.req_count);
     pool->launches++;
     return rc;
@@ -209,6 +213,15 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
     D.noise = cfg->noise ? 1 : 0;
     D.auto_play = cfg->auto_play ? 1 : 0;
     D.steps_per_tick = pool->cfg.steps_per_tick;
+    // evaluations per tick: a whole number of rounds of the net kernel's persistent CTAs (2 boards x 2 CTAs per SM),
+    // so its last round is never half empty; self-play only (search pools serve every request)
+    D.cap = D.G;
+    if (cfg->auto_play && cfg->eval_mode == AZ_NET_BF16) {
+        const int round = 4 * ctx->sm_count;
+        const char *env = getenv("AZ_REQ_CAP");
+        if (env) D.cap = atoi(env) > 0 ? std::min(atoi(env), D.G) : D.G;
+        else if (D.G >= round) D.cap = D.G / round * round;
+    }
     D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : 48;
     D.seed = cfg->seed;
     D.rec_cap_words = cfg->auto_play ? (uint32_t)pool->cfg.max_plies * kRecWordsPerPly : 16;
@@ -228,7 +241,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
     rc |= dev_alloc(&D.gstack, G * D.C, false);
     rc |= dev_alloc(&D.req_pos, G);
     rc |= dev_alloc(&D.req_game, G);
-    rc |= dev_alloc(&D.req_count, 2);
+    rc |= dev_alloc(&D.req_count, 4);
     rc |= dev_alloc(&D.logits, G * AZ_LOGITS);
     rc |= dev_alloc(&D.values, G);
     rc |= dev_alloc(&D.records, G * 2 * D.rec_cap_words, false);

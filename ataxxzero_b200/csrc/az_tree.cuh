@@ -85,7 +85,8 @@ struct PoolDev {
     uint32_t *gstack;        // [G][C]
     az_position *req_pos;    // [G]
     int32_t *req_game;       // [G]
-    int32_t *req_count;      // [2]: [0] requests of this tick, [1] games that still have work but made no request
+    int32_t *req_count;      // [3]: [0] requests of this tick, [1] games that still have work but made no request,
+                             //      [2] requests of the previous tick (of which the first `cap` were evaluated)
     float *logits;           // [G][833]
     float *values;           // [G]
     uint32_t *records;       // [G][2][rec_cap_words]
@@ -93,6 +94,7 @@ struct PoolDev {
     int32_t *done_count;     // [1]
     int32_t G, C, visits, max_plies, noise, auto_play, steps_per_tick;
     int32_t levels_per_tick; // bound on tree levels a game may descend per tick (tail latency of deep endgame lines)
+    int32_t cap;             // evaluations served per tick: a whole number of net-kernel rounds; later requests are re-queued
     int32_t consume;         // 1: evaluations of the previous requests are in logits/values; 0: top-up tick, leave waiting games alone
     uint32_t rec_cap_words;
     uint64_t seed;

@@ -1,5 +1,5 @@
-for lv in 16 32 48 96 100000; do
-AZ_LEVELS_PER_TICK=$lv timeout 200 python - <<PY
+for cfg in "48 0" "48 1776" "96 1776" "100000 1776" "64 1184" "100000 2048"; do set -- $cfg
+AZ_LEVELS_PER_TICK=$1 AZ_REQ_CAP=$2 timeout 200 python - <<PY
 import sys, os
 sys.path.insert(0, os.getcwd())
 import bench, ataxxzero_b200 as az
@@ -13,6 +13,6 @@ s0 = pool.stats(); import time; t0 = time.perf_counter()
 pool.selfplay_ticks(1024)
 dt = time.perf_counter() - t0; s1 = pool.stats()
 d = {k: s1[k] - s0[k] for k in s1}
-print("levels=%s: %.3f ms/tick tree %.3f net %.3f  pos/s %.0f evals/tick %.0f evals/s %.0f" % (os.environ["AZ_LEVELS_PER_TICK"], dt / 1024 * 1e3, d["tree_seconds"] / 1024 * 1e3, d["net_seconds"] / 1024 * 1e3, d["positions"] / dt, d["evals"] / 1024, d["evals"] / dt))
+print("levels=%s cap=%s: %.3f ms/tick tree %.3f net %.3f  pos/s %.0f evals/tick %.0f evals/s %.0f" % (os.environ["AZ_LEVELS_PER_TICK"], os.environ["AZ_REQ_CAP"], dt / 1024 * 1e3, d["tree_seconds"] / 1024 * 1e3, d["net_seconds"] / 1024 * 1e3, d["positions"] / dt, d["evals"] / 1024, d["evals"] / dt))
 PY
 done
