@@ -342,6 +342,22 @@ extern "C" int az_pool_set_roots(az_pool *pool, const az_position *roots)
     return check_game_errors(pool);
 }
 
+extern "C" int az_pool_set_visits(az_pool *pool, int visits)
+{
+    AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_set_visits: null pool");
+    AZ_REQUIRE(visits >= 1 && visits + 2 <= pool->dev.C, AZ_ERR_ARG, "az_pool_set_visits: visits=%d does not fit node_capacity=%d", visits,
+               pool->dev.C);
+    pool->dev.visits = visits;
+    pool->cfg.visits = visits;
+    // trees that were parked as "done" under the old target may have work again
+    AZ_CUDA(cudaStreamSynchronize(pool->ctx->stream));
+    AZ_CUDA(cudaMemcpy(pool->h_games.data(), pool->dev.games, sizeof(Game) * pool->dev.G, cudaMemcpyDeviceToHost));
+    for (Game &g : pool->h_games)
+        if (g.status == ST_DONE) g.status = ST_IDLE;
+    AZ_CUDA(cudaMemcpy(pool->dev.games, pool->h_games.data(), sizeof(Game) * pool->dev.G, cudaMemcpyHostToDevice));
+    return AZ_OK;
+}
+
 extern "C" int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out)
 {
     AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_run: null pool");

@@ -39,6 +39,7 @@ _native.register("az_pool_destroy", None, [_vp])
 _native.register("az_pool_stats_get", C.c_int, [_vp, C.POINTER(PoolStats)])
 _native.register("az_pool_set_root", C.c_int, [_vp, C.c_int, C.POINTER(Position)])
 _native.register("az_pool_set_roots", C.c_int, [_vp, _vp])
+_native.register("az_pool_set_visits", C.c_int, [_vp, C.c_int])
 _native.register("az_pool_run", C.c_int, [_vp, C.c_int, C.POINTER(C.c_int32)])
 _native.register("az_pool_collect", C.c_int, [_vp, _vp, C.POINTER(C.c_int32)])
 _native.register("az_pool_provide", C.c_int, [_vp, _vp, _vp])
@@ -96,6 +97,9 @@ class Pool:
         if len(arr) != self.games:
             raise AzError(-1, "set_roots: %d positions for %d games" % (len(arr), self.games))
         check(lib().az_pool_set_roots(self._h, C.c_void_p(arr.ctypes.data)))
+
+    def set_visits(self, visits):
+        check(lib().az_pool_set_visits(self._h, int(visits)))
 
     def run(self, max_ticks=1 << 30):
         """Internal net: tick until every tree reached its visit target; returns True when idle."""

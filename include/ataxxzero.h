@@ -160,6 +160,8 @@ int az_pool_stats_get(az_pool *pool, az_pool_stats *out);
 int az_pool_set_root(az_pool *pool, int game, const az_position *root);
 /* the same for every tree at once: roots is az_position[cfg.games] (host memory) */
 int az_pool_set_roots(az_pool *pool, const az_position *roots);
+/* change the visit target of every tree (MCTSEngine.MAX_STEPS / VISITS style control); must fit node_capacity */
+int az_pool_set_visits(az_pool *pool, int visits);
 /* Advance every tree with the internal net until each has root visits >= cfg.visits (search mode) or
  * `max_ticks` ticks have run.  *idle_out = 1 when no tree needs more work. */
 int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out);
