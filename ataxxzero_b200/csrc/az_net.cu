@@ -247,21 +247,22 @@ extern "C" int az_net_load(az_context *ctx, const float *packed, size_t count, i
 }
 
 static int net_forward_dev(az_context *ctx, const void *d_in, int in_kind, int n, int mode, void *d_logits, void *d_values,
-                           const int *d_count = nullptr)
+                           const int *d_count = nullptr, cudaStream_t stream = nullptr, int tiles = 0)
 {
+    if (!stream && ctx) stream = ctx->stream;
     AZ_REQUIRE(ctx && (n == 0 || (d_in && d_logits && d_values)), AZ_ERR_ARG, "az_net_forward: null argument");
     AZ_REQUIRE(ctx->net, AZ_ERR_STATE, "az_net_forward: no weights loaded (call az_net_load first)");
     AZ_REQUIRE(n >= 0, AZ_ERR_ARG, "az_net_forward: n=%d", n);
     AZ_REQUIRE(mode == AZ_NET_FP32 || mode == AZ_NET_BF16, AZ_ERR_ARG, "az_net_forward: unknown mode %d", mode);
     if (n == 0) return AZ_OK;
     if (mode == AZ_NET_BF16)
-        return az_net_tc_forward(ctx, ctx->net, d_in, in_kind, n, static_cast<float *>(d_logits), static_cast<float *>(d_values), d_count);
+        return az_net_tc_forward(ctx, ctx->net, d_in, in_kind, n, static_cast<float *>(d_logits), static_cast<float *>(d_values), d_count, stream, tiles);
     const int grid = (n + NB - 1) / NB;
     if (in_kind == AZ_IN_F32)
-        k_net_fp32<AZ_IN_F32><<<grid, THREADS, SMEM_FP32, ctx->stream>>>(d_in, n, d_count, *ctx->net, static_cast<float *>(d_logits),
+        k_net_fp32<AZ_IN_F32><<<grid, THREADS, SMEM_FP32, stream>>>(d_in, n, d_count, *ctx->net, static_cast<float *>(d_logits),
                                                                        static_cast<float *>(d_values));
     else
-        k_net_fp32<AZ_IN_POS><<<grid, THREADS, SMEM_FP32, ctx->stream>>>(d_in, n, d_count, *ctx->net, static_cast<float *>(d_logits),
+        k_net_fp32<AZ_IN_POS><<<grid, THREADS, SMEM_FP32, stream>>>(d_in, n, d_count, *ctx->net, static_cast<float *>(d_logits),
                                                                        static_cast<float *>(d_values));
     ctx->launches++;
     AZ_CUDA(cudaGetLastError());
@@ -269,9 +270,9 @@ static int net_forward_dev(az_context *ctx, const void *d_in, int in_kind, int n
 }
 
 int az_net_forward_internal(az_context *ctx, const void *d_in, int in_kind, int n, int mode, float *d_logits, float *d_values,
-                            const int *d_count)
+                            const int *d_count, cudaStream_t stream, int tiles)
 {
-    return net_forward_dev(ctx, d_in, in_kind, n, mode, d_logits, d_values, d_count);
+    return net_forward_dev(ctx, d_in, in_kind, n, mode, d_logits, d_values, d_count, stream, tiles);
 }
 
 extern "C" int az_net_forward_dev(az_context *ctx, const void *d_features, int n, int mode, void *d_logits, void *d_values)

@@ -35,11 +35,13 @@ struct AzNet {
 // az_net_tc.cu
 int az_net_tc_alloc(AzNet *net);
 int az_net_tc_prepare(az_context *ctx, AzNet *net);
+// `stream` = nullptr: the context stream; `tiles` = 0: the context's default kernel variant
 int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
-                      const int *d_count = nullptr);
+                      const int *d_count = nullptr, cudaStream_t stream = nullptr, int tiles = 0);
 // internal: forward over up to `n` boards; when d_count != nullptr the actual count is read on the device
 int az_net_forward_internal(az_context *ctx, const void *d_in, int in_kind, int n, int mode, float *d_logits, float *d_values,
-                            const int *d_count);
+                            const int *d_count, cudaStream_t stream = nullptr, int tiles = 0);
+int az_net_tc_boards_per_round(az_context *ctx, int tiles);   // boards one wave of persistent CTAs evaluates
 void az_net_tc_release(AzNet *net);
 
 enum { AZ_IN_F32 = 0, AZ_IN_POS = 1 };

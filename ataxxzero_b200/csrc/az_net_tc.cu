@@ -298,7 +298,10 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
                 push(P.w_stream, WIN_CHUNK0);
                 push(P.w_stream + WIN_CHUNK0, WIN_BYTES - WIN_CHUNK0);
-                for (int c = 0; c < nl * CHUNKS; ++c) push(tower + (size_t)c * STAGE_BYTES, STAGE_BYTES);
+                // every tile walks a layer's 18 chunks on its own (tile 1 runs one layer-time behind tile 0, see the issuer)
+                for (int l = 0; l < nl; ++l)
+                    for (int t = 0; t < TILES; ++t)
+                        for (int c = 0; c < CHUNKS; ++c) push(tower + ((size_t)l * CHUNKS + c) * STAGE_BYTES, STAGE_BYTES);
                 if (heads) push(head_w, WHEAD_BYTES);
             }
         }
@@ -340,31 +343,37 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                 const uint32_t b_lo0 = (uint32_t)make_desc(sbase + C::OFF_RING, W_LBO);
                 constexpr uint32_t A_KSTEP = (2 * C::ACT_LBO) >> 4, B_KSTEP = (2 * W_LBO) >> 4, A_HALF = (8 * C::ACT_LBO) >> 4;
                 for (int l = 0; l < nl; ++l) {
-                    for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + t), act_phase);
-                    act_phase ^= 1;
-                    tc_fence_after();
+                    // tower layer l is conv layer l+1.  The second conv of a block accumulates straight ON TOP of the
+                    // block's input (the fp32 residual stream kept in TMEM): the skip connection costs no TMEM read.
+                    const uint32_t onto_res = (uint32_t)(l & 1);
+                    const uint32_t d_col = tmem_base + (onto_res ? C::TM_RES : C::TM_ACC);
+                    // Tiles take turns on the tensor pipe, a whole layer each: while tile t's 72 MMAs run, the epilogue
+                    // warps of the other tile drain its previous layer, so the pipe never waits for an epilogue.
 #pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
+                    for (int t = 0; t < TILES; ++t) {
+                        mbar_wait(bar(B_ACT + t), act_phase);
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int s = it % STAGES;
-                            mbar_wait(bar(B_FULL + s), (it / STAGES) & 1);
-                            tc_fence_after();
-                            const uint32_t b_lo = b_lo0 + s * (STAGE_BYTES >> 4);
-                            // tap shift in rows == shift in 16-byte units of the start-address field
-                            const uint32_t a_lo = a_lo0 + half * A_HALF + (uint32_t)((tap / 3 - 1) * 8 + (tap % 3 - 1));
-#pragma unroll
-                            for (int t = 0; t < TILES; ++t) {
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int s = it % STAGES;
+                                mbar_wait(bar(B_FULL + s), (it / STAGES) & 1);
+                                tc_fence_after();
+                                const uint32_t b_lo = b_lo0 + s * (STAGE_BYTES >> 4);
+                                // tap shift in rows == shift in 16-byte units of the start-address field
+                                const uint32_t a_lo = a_lo0 + t * TILE_M + half * A_HALF + (uint32_t)((tap / 3 - 1) * 8 + (tap % 3 - 1));
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
-                                    umma_lo(tmem_base + C::TM_ACC + t * 128, a_lo + t * TILE_M + j * A_KSTEP, a_hi, b_lo + j * B_KSTEP, b_hi,
-                                            IDESC_128, (half | tap | j) != 0);
+                                    umma_lo(d_col + t * 128, a_lo + j * A_KSTEP, a_hi, b_lo + j * B_KSTEP, b_hi, IDESC_128,
+                                            onto_res | (uint32_t)((half | tap | j) != 0));
                                 if (half == 1 && tap == 8) umma_commit(bar(B_ACC + t));
+                                umma_commit(bar(B_EMPTY + s));
+                                ++it;
                             }
-                            umma_commit(bar(B_EMPTY + s));
-                            ++it;
                         }
                     }
+                    act_phase ^= 1;
                 }
                 // ---- heads: [128 rows x 128 ch] x [128 ch x 32] ----
                 for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + t), act_phase);
@@ -431,17 +440,19 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                 mbar_wait(bar(B_ACC + tile), acc_phase);
                 acc_phase ^= 1;
                 tc_fence_after();
-#pragma unroll 1
-                for (int q = 0; q < 4; ++q) {          // 32 channels at a time
-                    uint32_t a[32];
-                    tmem_ld32(lane_addr + C::TM_ACC + tile * 128 + q * 32, a);
-                    uint32_t res[32];
-                    if (second) tmem_ld32(lane_addr + C::TM_RES + tile * 128 + q * 32, res);
+                // 32 channels at a time, TMEM loads software-pipelined one step ahead of the arithmetic.  For the second
+                // conv of a block the accumulator already contains the residual (see the MMA issuer).
+                const uint32_t src = lane_addr + (second ? C::TM_RES : C::TM_ACC) + tile * 128;
+                uint32_t acc[2][32];
+                tmem_ld32(src, acc[0]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t (&a)[32] = acc[q & 1];
                     tmem_wait_ld();
+                    if (q < 3) tmem_ld32(src + (q + 1) * 32, acc[(q + 1) & 1]);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         float v = __uint_as_float(a[i]) + shift_s[q * 32 + i];
-                        if (second) v += __uint_as_float(res[i]);
                         v = live ? fmaxf(v, 0.f) : 0.f;
                         a[i] = __float_as_uint(v);
                     }
@@ -593,21 +604,32 @@ void az_net_tc_release(AzNet *net)
 }
 
 template <int TILES>
-static void tc_launch_variant(az_context *ctx, const TcParams &P, int in_kind, int n)
+static void tc_launch_variant(az_context *ctx, const TcParams &P, int in_kind, int n, cudaStream_t stream)
 {
     using C = Cfg<TILES>;
     const int units = (n + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS;
-    const int slots = ctx->sm_count * C::CTAS_PER_SM;
+    int slots = ctx->sm_count * C::CTAS_PER_SM;
+    if (const char *env = getenv("AZ_NET_MAX_CTAS")) slots = std::max(1, std::min(slots, atoi(env)));     // experiment knob
     const int grid = units < slots ? units : slots;
     if (in_kind == AZ_IN_F32)
-        k_net_tc<TILES, AZ_IN_F32><<<grid, C::NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(P);
+        k_net_tc<TILES, AZ_IN_F32><<<grid, C::NUM_THREADS, C::SMEM_BYTES, stream>>>(P);
     else
-        k_net_tc<TILES, AZ_IN_POS><<<grid, C::NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(P);
+        k_net_tc<TILES, AZ_IN_POS><<<grid, C::NUM_THREADS, C::SMEM_BYTES, stream>>>(P);
+}
+
+int az_net_tc_boards_per_round(az_context *ctx, int tiles)
+{
+    if (tiles == 0) tiles = ctx->net ? ctx->net->tc_tiles : AZ_NET_TILES_DEFAULT;
+    int slots = tiles == 1 ? ctx->sm_count * Cfg<1>::CTAS_PER_SM : ctx->sm_count * Cfg<2>::CTAS_PER_SM;
+    if (const char *env = getenv("AZ_NET_MAX_CTAS")) slots = std::max(1, std::min(slots, atoi(env)));
+    return slots * (tiles == 1 ? Cfg<1>::UNIT_BOARDS : Cfg<2>::UNIT_BOARDS);
 }
 
 static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
-                     int debug_layers, float *d_debug, const int *d_count = nullptr)
+                     int debug_layers, float *d_debug, const int *d_count = nullptr, cudaStream_t stream = nullptr, int tiles = 0)
 {
+    if (!stream) stream = ctx->stream;
+    if (tiles == 0) tiles = net->tc_tiles;
     TcParams P;
     P.input = d_in;
     P.n = n;
@@ -621,17 +643,17 @@ static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind,
     P.logits = d_logits;
     P.values = d_values;
     P.debug_act = d_debug;
-    if (net->tc_tiles == 1) tc_launch_variant<1>(ctx, P, in_kind, n);
-    else tc_launch_variant<2>(ctx, P, in_kind, n);
+    if (tiles == 1) tc_launch_variant<1>(ctx, P, in_kind, n, stream);
+    else tc_launch_variant<2>(ctx, P, in_kind, n, stream);
     ctx->launches++;
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
 
 int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
-                      const int *d_count)
+                      const int *d_count, cudaStream_t stream, int tiles)
 {
-    return tc_launch(ctx, net, d_in, in_kind, n, d_logits, d_values, -1, nullptr, d_count);
+    return tc_launch(ctx, net, d_in, in_kind, n, d_logits, d_values, -1, nullptr, d_count, stream, tiles);
 }
 
 // Debug/validation hook (not part of the public header): run the first `conv_layers` convolutions of the

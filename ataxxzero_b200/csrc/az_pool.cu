@@ -24,11 +24,19 @@ void aztree_launch_play(const PoolDev &P, int g, int move, int *d_status, cudaSt
 void aztree_launch_release(const PoolDev &P, const DoneEntry *d_done, int n, cudaStream_t s);
 void aztree_launch_features(const az_position *d_pos, int n, float *d_out, cudaStream_t s);
 
-struct az_pool {
-    az_context *ctx = nullptr;
-    az_pool_config cfg{};
+// A pool is split into GROUPS of games, each with its own tree memory, request batch and CUDA stream.  With two
+// groups the tree kernel of one group runs while the net kernel evaluates the other group's leaves: the net kernel
+// is tensor-pipe bound and leaves registers / shared memory / issue slots for the latency-bound tree warps, so
+// the tree time disappears behind the net time (self-play with the internal net only; search and external-
+// evaluator pools use one group on the context stream).
+const int kTicksPerDrain = 32;
+
+struct Group {
     PoolDev dev{};
-    size_t node_bytes = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int first_game = 0;
+    int slot = 0;                         // req_count slot of the last tick
     int32_t *d_status = nullptr;
     float *d_features = nullptr;          // external mode: [G][196]
     DoneEntry *d_done_snapshot = nullptr; // copy of the done queue being drained
@@ -37,11 +45,31 @@ struct az_pool {
     DoneEntry *h_done = nullptr;          // [2G]
     uint32_t *h_record = nullptr;         // one record buffer
     std::vector<Game> h_games;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // AZ_POOL_TRACE=1: events around every kernel of every tick (as scheduled, i.e. with the groups overlapping)
+    std::vector<cudaEvent_t> trace;       // [kTicksPerDrain][3]
+    double trace_tree_ms = 0, trace_net_ms = 0, trace_gap_ms = 0;
+    uint64_t trace_n = 0;
+};
+
+struct az_pool {
+    az_context *ctx = nullptr;
+    az_pool_config cfg{};
+    std::vector<Group> groups;
+    int per_group = 0;                    // games per group (the last group may hold fewer)
+    int net_tiles = 0;                    // net kernel variant used by this pool (0 = context default)
     int pending_requests = 0;             // external mode: requests handed out by collect()
     uint64_t ticks = 0, launches = 0;
     double net_seconds = 0.0, tree_seconds = 0.0;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     uint64_t written_games = 0, written_positions = 0, d2h_bytes = 0;
+
+    Group &group_of(int game, int *local)
+    {
+        const int gi = game / per_group;
+        *local = game - gi * per_group;
+        return groups[gi];
+    }
+    int G() const { return cfg.games; }
 };
 
 namespace {
@@ -56,39 +84,45 @@ int dev_alloc(T **p, size_t count, bool zero = true)
 
 const char *kErrNames[] = {"", "node pool exhausted", "selection path longer than 1024 plies", ">= 256 legal moves"};
 
+int sync_all(az_pool *pool)
+{
+    AZ_CUDA(cudaStreamSynchronize(pool->ctx->stream));
+    for (Group &g : pool->groups)
+        if (g.own_stream) AZ_CUDA(cudaStreamSynchronize(g.stream));
+    return AZ_OK;
+}
+
 int check_game_errors(az_pool *pool)
 {
     // called after a sync: any game in ST_ERROR turns into AZ_ERR_CAPACITY
-    AZ_CUDA(cudaMemcpy(pool->h_games.data(), pool->dev.games, sizeof(Game) * pool->dev.G, cudaMemcpyDeviceToHost));
-    for (int g = 0; g < pool->dev.G; ++g)
-        if (pool->h_games[g].status == ST_ERROR)
-            return az_fail(AZ_ERR_CAPACITY, "game %d: %s", g, kErrNames[std::min(std::max(pool->h_games[g].error, 0), 3)]);
+    for (Group &grp : pool->groups) {
+        AZ_CUDA(cudaMemcpy(grp.h_games.data(), grp.dev.games, sizeof(Game) * grp.dev.G, cudaMemcpyDeviceToHost));
+        for (int g = 0; g < grp.dev.G; ++g)
+            if (grp.h_games[g].status == ST_ERROR)
+                return az_fail(AZ_ERR_CAPACITY, "game %d: %s", grp.first_game + g, kErrNames[std::min(std::max(grp.h_games[g].error, 0), 3)]);
+    }
     return AZ_OK;
 }
 
 // ---- one tick: (previous evaluations ->) tree kernel -> requests ----
-int launch_tree(az_pool *pool, bool consume = true)
+int launch_tree(az_pool *pool, Group &grp, bool consume = true)
 {
-    cudaStream_t s = pool->ctx->stream;
-    if (consume) {
-        AZ_CUDA(cudaMemcpyAsync(pool->dev.req_count + 2, pool->dev.req_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
-        AZ_CUDA(cudaMemsetAsync(pool->dev.req_count, 0, 2 * sizeof(int32_t), s));
-    } else {
-        AZ_CUDA(cudaMemsetAsync(pool->dev.req_count + 1, 0, sizeof(int32_t), s));
-    }
-    pool->dev.consume = consume ? 1 : 0;
-    aztree_launch_tick(pool->dev, s);
-    pool->ticks++;
+    cudaStream_t s = grp.stream;
+    if (consume) grp.slot = (grp.slot + 1) % 3;          // the kernel itself zeroes the slot after this one
+    else AZ_CUDA(cudaMemsetAsync(grp.dev.req_count + 2 * grp.slot + 1, 0, sizeof(int32_t), s));   // top-up: same slot, fresh busy count
+    grp.dev.consume = consume ? 1 : 0;
+    grp.dev.tick_slot = grp.slot;
+    aztree_launch_tick(grp.dev, s);
     pool->launches++;
     pool->ctx->launches++;
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
 
-int launch_net(az_pool *pool)
+int launch_net(az_pool *pool, Group &grp)
 {
-    int rc = az_net_forward_internal(pool->ctx, pool->dev.req_pos, AZ_IN_POS, pool->dev.cap, pool->cfg.eval_mode, pool->dev.logits,
-                                     pool->dev.values, pool->dev.req_count);
+    int rc = az_net_forward_internal(pool->ctx, grp.dev.req_pos, AZ_IN_POS, grp.dev.cap, pool->cfg.eval_mode, grp.dev.logits,
+                                     grp.dev.values, grp.dev.req_count + 2 * grp.slot, grp.stream, pool->net_tiles);
     pool->launches++;
     return rc;
 }
@@ -145,28 +179,28 @@ std::string record_to_json(const uint32_t *rec, int words, int plies, int result
     return "{\"boards\":" + boards + "],\"dists\":" + dists + "],\"moves\":" + moves + "],\"result\":" + std::to_string(result) + "}";
 }
 
-// copy out finished games, append them to `out` (may be null: records are dropped), release the buffers
-int drain_finished(az_pool *pool, FILE *out, int64_t *games_written, bool copy_payload = true)
+// copy out a group's finished games, append them to `out` (may be null: records are dropped), release the buffers
+int drain_finished(az_pool *pool, Group &grp, FILE *out, int64_t *games_written, bool copy_payload = true)
 {
-    cudaStream_t s = pool->ctx->stream;
-    AZ_CUDA(cudaMemcpyAsync(pool->h_counts + 3, pool->dev.done_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    cudaStream_t s = grp.stream;
+    AZ_CUDA(cudaMemcpyAsync(grp.h_counts + 3, grp.dev.done_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
-    const int n = pool->h_counts[3];
+    const int n = grp.h_counts[3];
     if (n == 0) return AZ_OK;
-    AZ_CUDA(cudaMemcpyAsync(pool->h_done, pool->dev.done, sizeof(DoneEntry) * n, cudaMemcpyDeviceToHost, s));
-    AZ_CUDA(cudaMemcpyAsync(pool->d_done_snapshot, pool->dev.done, sizeof(DoneEntry) * n, cudaMemcpyDeviceToDevice, s));
-    AZ_CUDA(cudaMemsetAsync(pool->dev.done_count, 0, sizeof(int32_t), s));
+    AZ_CUDA(cudaMemcpyAsync(grp.h_done, grp.dev.done, sizeof(DoneEntry) * n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(grp.d_done_snapshot, grp.dev.done, sizeof(DoneEntry) * n, cudaMemcpyDeviceToDevice, s));
+    AZ_CUDA(cudaMemsetAsync(grp.dev.done_count, 0, sizeof(int32_t), s));
     AZ_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < n; ++i) {
-        const DoneEntry &d = pool->h_done[i];
-        const uint32_t *src = pool->dev.records + ((size_t)d.game * 2 + d.buf) * pool->dev.rec_cap_words;
+        const DoneEntry &d = grp.h_done[i];
+        const uint32_t *src = grp.dev.records + ((size_t)d.game * 2 + d.buf) * grp.dev.rec_cap_words;
         if (copy_payload) {
-            AZ_CUDA(cudaMemcpyAsync(pool->h_record, src, sizeof(uint32_t) * d.words, cudaMemcpyDeviceToHost, s));
+            AZ_CUDA(cudaMemcpyAsync(grp.h_record, src, sizeof(uint32_t) * d.words, cudaMemcpyDeviceToHost, s));
             AZ_CUDA(cudaStreamSynchronize(s));
             pool->d2h_bytes += sizeof(uint32_t) * (uint64_t)d.words;
         }
         if (out && copy_payload) {
-            const std::string line = record_to_json(pool->h_record, d.words, d.plies, d.result);
+            const std::string line = record_to_json(grp.h_record, d.words, d.plies, d.result);
             if (fwrite(line.data(), 1, line.size(), out) != line.size() || fputc('\n', out) == EOF)
                 return az_fail(AZ_ERR_IO, "short write to the game file");
             fflush(out);                                              // one flushed line per game (:641-642)
@@ -175,9 +209,31 @@ int drain_finished(az_pool *pool, FILE *out, int64_t *games_written, bool copy_p
         pool->written_positions += d.plies;
         if (games_written) (*games_written)++;
     }
-    aztree_launch_release(pool->dev, pool->d_done_snapshot, n, s);
+    aztree_launch_release(grp.dev, grp.d_done_snapshot, n, s);
     pool->launches++;
     return AZ_OK;
+}
+
+void free_group(Group &grp)
+{
+    PoolDev &D = grp.dev;
+    void *ptrs[] = {D.nodes, D.games, D.path, D.gstack, D.req_pos, D.req_game, D.req_count, D.logits, D.values, D.records,
+                    D.done, D.done_count, grp.d_done_snapshot, grp.d_status, grp.d_features};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (grp.h_counts) cudaFreeHost(grp.h_counts);
+    if (grp.h_done) cudaFreeHost(grp.h_done);
+    if (grp.h_record) cudaFreeHost(grp.h_record);
+    for (auto &e : grp.ev)
+        if (e) cudaEventDestroy(e);
+    if (grp.own_stream && grp.stream) cudaStreamDestroy(grp.stream);
+    grp = Group();
+}
+
+bool valid_position(const az_position &r)
+{
+    const uint64_t all = r.pieces[0] | r.pieces[1] | r.blockers;
+    return !(r.pieces[0] & r.pieces[1]) && !((r.pieces[0] | r.pieces[1]) & r.blockers) && !(all >> 49) && (r.pieces[0] | r.pieces[1]);
 }
 
 }  // namespace
@@ -205,60 +261,99 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
     if (pool->cfg.node_capacity <= 0) pool->cfg.node_capacity = cfg->visits + 64;
     if (pool->cfg.steps_per_tick <= 0) pool->cfg.steps_per_tick = 8;
     AZ_REQUIRE(pool->cfg.node_capacity < (1 << 24), AZ_ERR_ARG, "az_pool_create: node_capacity too large");
-    PoolDev &D = pool->dev;
-    D.G = cfg->games;
-    D.C = pool->cfg.node_capacity;
-    D.visits = cfg->visits;
-    D.max_plies = pool->cfg.max_plies;
-    D.noise = cfg->noise ? 1 : 0;
-    D.auto_play = cfg->auto_play ? 1 : 0;
-    D.steps_per_tick = pool->cfg.steps_per_tick;
-    // evaluations per tick: a whole number of rounds of the net kernel's persistent CTAs (2 boards x 2 CTAs per SM),
-    // so its last round is never half empty; self-play only (search pools serve every request)
-    D.cap = D.G;
-    if (cfg->auto_play && cfg->eval_mode == AZ_NET_BF16) {
-        const int round = 4 * ctx->sm_count;
-        const char *env = getenv("AZ_REQ_CAP");
-        if (env) D.cap = atoi(env) > 0 ? std::min(atoi(env), D.G) : D.G;
-        else if (D.G >= round) D.cap = D.G / round * round;
+
+    // Self-play on the internal tensor-core net: two groups that take turns on the net kernel (see Group).  The
+    // 2-tile net variant (one CTA per SM) is used there because it leaves room for the tree blocks on every SM.
+    const bool pipelined = cfg->auto_play && cfg->eval_mode == AZ_NET_BF16;
+    int n_groups = 1;
+    if (pipelined) {
+        const char *env = getenv("AZ_POOL_GROUPS");
+        const int round1 = az_net_tc_boards_per_round(ctx, 0);
+        // Measured on B200 (2048 games x 800 visits): a tree kernel that shares the SMs with the net kernel runs ~2.2x
+        // slower (the net streams ~12 TB/s of weights out of L2), which eats the overlap: 2 groups give 2.50 M
+        // evaluations/s against 2.69 M for one group with whole-round request batches.  So: opt-in (AZ_POOL_GROUPS=2).
+        (void)round1;
+        n_groups = env ? std::max(1, std::min(atoi(env), 4)) : 1;
+        n_groups = std::min(n_groups, cfg->games);
+        const char *tiles_env = getenv("AZ_POOL_NET_TILES");
+        if (tiles_env) pool->net_tiles = atoi(tiles_env) == 1 ? 1 : atoi(tiles_env) == 2 ? 2 : 0;
     }
-    D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : 48;
-    D.seed = cfg->seed;
-    D.rec_cap_words = cfg->auto_play ? (uint32_t)pool->cfg.max_plies * kRecWordsPerPly : 16;
-    const size_t G = (size_t)D.G;
-    pool->node_bytes = G * D.C * kNodeStride;
+    pool->per_group = (cfg->games + n_groups - 1) / n_groups;
+    pool->groups.resize(n_groups);
+
     size_t free_b = 0, total_b = 0;
     AZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t need = pool->node_bytes + G * 2 * D.rec_cap_words * 4 + G * (kMaxPath + D.C) * 4 + G * 4096;
-    if (need > free_b) {
-        delete pool;
-        return az_fail(AZ_ERR_CAPACITY, "az_pool_create: needs %.1f GiB of HBM, %.1f GiB free", need / 1073741824.0, free_b / 1073741824.0);
+    const uint32_t rec_cap_words = cfg->auto_play ? (uint32_t)pool->cfg.max_plies * kRecWordsPerPly : 16;
+    {
+        const size_t G = (size_t)cfg->games, C = (size_t)pool->cfg.node_capacity;
+        const size_t need = G * C * kNodeStride + G * 2 * rec_cap_words * 4 + G * (kMaxPath + C) * 4 + G * 4096;
+        if (need > free_b) {
+            delete pool;
+            return az_fail(AZ_ERR_CAPACITY, "az_pool_create: needs %.1f GiB of HBM, %.1f GiB free", need / 1073741824.0, free_b / 1073741824.0);
+        }
     }
     int rc = 0;
-    rc |= dev_alloc(&D.nodes, pool->node_bytes, false);
-    rc |= dev_alloc(&D.games, G);
-    rc |= dev_alloc(&D.path, G * kMaxPath, false);
-    rc |= dev_alloc(&D.gstack, G * D.C, false);
-    rc |= dev_alloc(&D.req_pos, G);
-    rc |= dev_alloc(&D.req_game, G);
-    rc |= dev_alloc(&D.req_count, 4);
-    rc |= dev_alloc(&D.logits, G * AZ_LOGITS);
-    rc |= dev_alloc(&D.values, G);
-    rc |= dev_alloc(&D.records, G * 2 * D.rec_cap_words, false);
-    rc |= dev_alloc(&D.done, 2 * G);
-    rc |= dev_alloc(&D.done_count, 1);
-    rc |= dev_alloc(&pool->d_done_snapshot, 2 * G);
-    rc |= dev_alloc(&pool->d_status, 4);
-    rc |= dev_alloc(&pool->d_features, G * AZ_FEATURES);
-    if (rc) { az_pool_destroy(pool); return AZ_ERR_CUDA; }
-    AZ_CUDA(cudaMallocHost(&pool->h_counts, 16 * sizeof(int32_t)));
-    AZ_CUDA(cudaMallocHost(&pool->h_done, sizeof(DoneEntry) * 2 * G));
-    AZ_CUDA(cudaMallocHost(&pool->h_record, sizeof(uint32_t) * D.rec_cap_words));
-    pool->h_games.resize(G);
-    for (auto &e : pool->ev) AZ_CUDA(cudaEventCreate(&e));
-    aztree_launch_init_all(D, start, ctx->stream);
-    pool->launches++;
-    AZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int gi = 0; gi < n_groups && rc == 0; ++gi) {
+        Group &grp = pool->groups[gi];
+        grp.first_game = gi * pool->per_group;
+        PoolDev &D = grp.dev;
+        D.G = std::min(pool->per_group, cfg->games - grp.first_game);
+        D.C = pool->cfg.node_capacity;
+        D.visits = cfg->visits;
+        D.max_plies = pool->cfg.max_plies;
+        D.noise = cfg->noise ? 1 : 0;
+        D.auto_play = cfg->auto_play ? 1 : 0;
+        D.steps_per_tick = pool->cfg.steps_per_tick;
+        D.game_base = grp.first_game;
+        // evaluations per tick: a whole number of rounds of the net kernel's persistent CTAs, so its last round is
+        // never half empty; later requests are re-queued.  Self-play only (search pools serve every request).
+        D.cap = D.G;
+        if (pipelined) {
+            const int round = az_net_tc_boards_per_round(ctx, pool->net_tiles);
+            const char *env = getenv("AZ_REQ_CAP");
+            if (env) D.cap = atoi(env) > 0 ? std::min(atoi(env), D.G) : D.G;
+            else if (D.G >= round) D.cap = D.G / round * round;
+        }
+        D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : 48;
+        D.seed = cfg->seed;
+        D.rec_cap_words = rec_cap_words;
+        const size_t G = (size_t)D.G;
+        rc |= dev_alloc(&D.nodes, G * D.C * kNodeStride, false);
+        rc |= dev_alloc(&D.games, G);
+        rc |= dev_alloc(&D.path, G * kMaxPath, false);
+        rc |= dev_alloc(&D.gstack, G * D.C, false);
+        rc |= dev_alloc(&D.req_pos, G);
+        rc |= dev_alloc(&D.req_game, G);
+        rc |= dev_alloc(&D.req_count, 8);
+        rc |= dev_alloc(&D.logits, G * AZ_LOGITS);
+        rc |= dev_alloc(&D.values, G);
+        rc |= dev_alloc(&D.records, G * 2 * D.rec_cap_words, false);
+        rc |= dev_alloc(&D.done, 2 * G);
+        rc |= dev_alloc(&D.done_count, 1);
+        rc |= dev_alloc(&grp.d_done_snapshot, 2 * G);
+        rc |= dev_alloc(&grp.d_status, 4);
+        rc |= dev_alloc(&grp.d_features, G * AZ_FEATURES);
+        if (rc) break;
+        if (cudaMallocHost(&grp.h_counts, 16 * sizeof(int32_t)) != cudaSuccess || cudaMallocHost(&grp.h_done, sizeof(DoneEntry) * 2 * G) != cudaSuccess ||
+            cudaMallocHost(&grp.h_record, sizeof(uint32_t) * D.rec_cap_words) != cudaSuccess) { rc = az_fail(AZ_ERR_CUDA, "az_pool_create: pinned host alloc"); break; }
+        grp.h_games.resize(G);
+        for (auto &e : grp.ev)
+            if (cudaEventCreate(&e) != cudaSuccess) rc = az_fail(AZ_ERR_CUDA, "az_pool_create: event");
+        if (n_groups > 1) {
+            if (cudaStreamCreateWithFlags(&grp.stream, cudaStreamNonBlocking) != cudaSuccess) { rc = az_fail(AZ_ERR_CUDA, "az_pool_create: stream"); break; }
+            grp.own_stream = true;
+        } else {
+            grp.stream = ctx->stream;
+        }
+        if (getenv("AZ_POOL_TRACE")) {
+            grp.trace.resize(3 * kTicksPerDrain);
+            for (auto &e : grp.trace) cudaEventCreate(&e);
+        }
+        aztree_launch_init_all(D, start, grp.stream);
+        pool->launches++;
+    }
+    if (rc) { az_pool_destroy(pool); return rc ? rc : AZ_ERR_CUDA; }
+    if ((rc = sync_all(pool))) { az_pool_destroy(pool); return rc; }
     AZ_CUDA(cudaGetLastError());
     if ((rc = check_game_errors(pool))) { az_pool_destroy(pool); return rc; }
     *out = pool;
@@ -269,33 +364,36 @@ extern "C" void az_pool_destroy(az_pool *pool)
 {
     if (!pool) return;
     cudaStreamSynchronize(pool->ctx->stream);
-    PoolDev &D = pool->dev;
-    void *ptrs[] = {D.nodes, D.games, D.path, D.gstack, D.req_pos, D.req_game, D.req_count, D.logits, D.values, D.records,
-                    D.done, D.done_count, pool->d_done_snapshot, pool->d_status, pool->d_features};
-    for (void *p : ptrs)
-        if (p) cudaFree(p);
-    if (pool->h_counts) cudaFreeHost(pool->h_counts);
-    if (pool->h_done) cudaFreeHost(pool->h_done);
-    if (pool->h_record) cudaFreeHost(pool->h_record);
-    for (auto &e : pool->ev)
-        if (e) cudaEventDestroy(e);
+    for (Group &grp : pool->groups) {
+        if (grp.stream) cudaStreamSynchronize(grp.stream);
+        if (grp.trace_n)
+            fprintf(stderr, "[az_pool trace] group@%d: tree %.3f ms, net %.3f ms (launch to completion, overlapped), idle gap %.3f ms, %llu ticks\n",
+                    grp.first_game, grp.trace_tree_ms / grp.trace_n, grp.trace_net_ms / grp.trace_n, grp.trace_gap_ms / grp.trace_n,
+                    (unsigned long long)grp.trace_n);
+        for (auto &e : grp.trace) cudaEventDestroy(e);
+        grp.trace.clear();
+        free_group(grp);
+    }
     delete pool;
 }
 
 extern "C" int az_pool_stats_get(az_pool *pool, az_pool_stats *out)
 {
     AZ_REQUIRE(pool && out, AZ_ERR_ARG, "az_pool_stats_get: null argument");
-    AZ_CUDA(cudaStreamSynchronize(pool->ctx->stream));
-    AZ_CUDA(cudaMemcpy(pool->h_games.data(), pool->dev.games, sizeof(Game) * pool->dev.G, cudaMemcpyDeviceToHost));
+    int rc = sync_all(pool);
+    if (rc) return rc;
     az_pool_stats s{};
-    for (const Game &g : pool->h_games) {
-        s.steps += g.steps;
-        s.evals += g.evals;
-        s.terminal_steps += g.terminal_steps;
-        s.positions += g.positions;
-        s.games_finished += g.finished;
-        s.games_skipped += g.skipped;
-        s.max_depth = std::max<uint64_t>(s.max_depth, g.max_depth);
+    for (Group &grp : pool->groups) {
+        AZ_CUDA(cudaMemcpy(grp.h_games.data(), grp.dev.games, sizeof(Game) * grp.dev.G, cudaMemcpyDeviceToHost));
+        for (const Game &g : grp.h_games) {
+            s.steps += g.steps;
+            s.evals += g.evals;
+            s.terminal_steps += g.terminal_steps;
+            s.positions += g.positions;
+            s.games_finished += g.finished;
+            s.games_skipped += g.skipped;
+            s.max_depth = std::max<uint64_t>(s.max_depth, g.max_depth);
+        }
     }
     s.ticks = pool->ticks;
     s.kernel_launches = pool->launches;
@@ -309,15 +407,14 @@ extern "C" int az_pool_stats_get(az_pool *pool, az_pool_stats *out)
 extern "C" int az_pool_set_root(az_pool *pool, int game, const az_position *root)
 {
     AZ_REQUIRE(pool && root, AZ_ERR_ARG, "az_pool_set_root: null argument");
-    AZ_REQUIRE(game >= 0 && game < pool->dev.G, AZ_ERR_ARG, "az_pool_set_root: game %d out of range", game);
+    AZ_REQUIRE(game >= 0 && game < pool->G(), AZ_ERR_ARG, "az_pool_set_root: game %d out of range", game);
     AZ_REQUIRE(pool->pending_requests == 0, AZ_ERR_STATE, "az_pool_set_root: evaluations are outstanding (az_pool_provide first)");
-    const uint64_t all = root->pieces[0] | root->pieces[1] | root->blockers;
-    AZ_REQUIRE(!(root->pieces[0] & root->pieces[1]) && !((root->pieces[0] | root->pieces[1]) & root->blockers) &&
-                   !(all >> 49) && (root->pieces[0] | root->pieces[1]),
-               AZ_ERR_ARG, "az_pool_set_root: invalid position");
-    aztree_launch_set_root(pool->dev, game, *root, pool->ctx->stream);
+    AZ_REQUIRE(valid_position(*root), AZ_ERR_ARG, "az_pool_set_root: invalid position");
+    int local;
+    Group &grp = pool->group_of(game, &local);
+    aztree_launch_set_root(grp.dev, local, *root, grp.stream);
     pool->launches++;
-    AZ_CUDA(cudaStreamSynchronize(pool->ctx->stream));
+    AZ_CUDA(cudaStreamSynchronize(grp.stream));
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
@@ -326,18 +423,16 @@ extern "C" int az_pool_set_roots(az_pool *pool, const az_position *roots)
 {
     AZ_REQUIRE(pool && roots, AZ_ERR_ARG, "az_pool_set_roots: null argument");
     AZ_REQUIRE(pool->pending_requests == 0, AZ_ERR_STATE, "az_pool_set_roots: evaluations are outstanding (az_pool_provide first)");
-    for (int g = 0; g < pool->dev.G; ++g) {
-        const az_position &r = roots[g];
-        const uint64_t all = r.pieces[0] | r.pieces[1] | r.blockers;
-        AZ_REQUIRE(!(r.pieces[0] & r.pieces[1]) && !((r.pieces[0] | r.pieces[1]) & r.blockers) && !(all >> 49) &&
-                       (r.pieces[0] | r.pieces[1]),
-                   AZ_ERR_ARG, "az_pool_set_roots: invalid position for game %d", g);
+    for (int g = 0; g < pool->G(); ++g)
+        AZ_REQUIRE(valid_position(roots[g]), AZ_ERR_ARG, "az_pool_set_roots: invalid position for game %d", g);
+    for (Group &grp : pool->groups) {
+        cudaStream_t s = grp.stream;
+        AZ_CUDA(cudaMemcpyAsync(grp.dev.req_pos, roots + grp.first_game, sizeof(az_position) * grp.dev.G, cudaMemcpyHostToDevice, s));
+        aztree_launch_set_roots(grp.dev, grp.dev.req_pos, s);     // req_pos is free between ticks: reuse it as staging
+        pool->launches++;
     }
-    cudaStream_t s = pool->ctx->stream;
-    AZ_CUDA(cudaMemcpyAsync(pool->dev.req_pos, roots, sizeof(az_position) * pool->dev.G, cudaMemcpyHostToDevice, s));
-    aztree_launch_set_roots(pool->dev, pool->dev.req_pos, s);     // req_pos is free between ticks: reuse it as staging
-    pool->launches++;
-    AZ_CUDA(cudaStreamSynchronize(s));
+    int rc = sync_all(pool);
+    if (rc) return rc;
     AZ_CUDA(cudaGetLastError());
     return check_game_errors(pool);
 }
@@ -345,16 +440,19 @@ extern "C" int az_pool_set_roots(az_pool *pool, const az_position *roots)
 extern "C" int az_pool_set_visits(az_pool *pool, int visits)
 {
     AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_set_visits: null pool");
-    AZ_REQUIRE(visits >= 1 && visits + 2 <= pool->dev.C, AZ_ERR_ARG, "az_pool_set_visits: visits=%d does not fit node_capacity=%d", visits,
-               pool->dev.C);
-    pool->dev.visits = visits;
+    AZ_REQUIRE(visits >= 1 && visits + 2 <= pool->cfg.node_capacity, AZ_ERR_ARG, "az_pool_set_visits: visits=%d does not fit node_capacity=%d",
+               visits, pool->cfg.node_capacity);
+    int rc = sync_all(pool);
+    if (rc) return rc;
     pool->cfg.visits = visits;
-    // trees that were parked as "done" under the old target may have work again
-    AZ_CUDA(cudaStreamSynchronize(pool->ctx->stream));
-    AZ_CUDA(cudaMemcpy(pool->h_games.data(), pool->dev.games, sizeof(Game) * pool->dev.G, cudaMemcpyDeviceToHost));
-    for (Game &g : pool->h_games)
-        if (g.status == ST_DONE) g.status = ST_IDLE;
-    AZ_CUDA(cudaMemcpy(pool->dev.games, pool->h_games.data(), sizeof(Game) * pool->dev.G, cudaMemcpyHostToDevice));
+    for (Group &grp : pool->groups) {
+        grp.dev.visits = visits;
+        // trees that were parked as "done" under the old target may have work again
+        AZ_CUDA(cudaMemcpy(grp.h_games.data(), grp.dev.games, sizeof(Game) * grp.dev.G, cudaMemcpyDeviceToHost));
+        for (Game &g : grp.h_games)
+            if (g.status == ST_DONE) g.status = ST_IDLE;
+        AZ_CUDA(cudaMemcpy(grp.dev.games, grp.h_games.data(), sizeof(Game) * grp.dev.G, cudaMemcpyHostToDevice));
+    }
     return AZ_OK;
 }
 
@@ -362,15 +460,21 @@ extern "C" int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out)
 {
     AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_run: null pool");
     AZ_REQUIRE(pool->cfg.eval_mode != AZ_EVAL_EXTERNAL, AZ_ERR_STATE, "az_pool_run: pool uses an external evaluator (collect/provide)");
-    cudaStream_t s = pool->ctx->stream;
     if (idle_out) *idle_out = 0;
     for (int t = 0; t < max_ticks; ++t) {
-        int rc = launch_tree(pool);
-        if (rc) return rc;
-        AZ_CUDA(cudaMemcpyAsync(pool->h_counts, pool->dev.req_count, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        if ((rc = launch_net(pool))) return rc;
-        AZ_CUDA(cudaStreamSynchronize(s));
-        if (pool->h_counts[0] == 0 && pool->h_counts[1] == 0) {   // no requests, nobody mid-step: every tree is done (or stalled)
+        bool idle = true;
+        for (Group &grp : pool->groups) {
+            int rc = launch_tree(pool, grp);
+            if (rc) return rc;
+            AZ_CUDA(cudaMemcpyAsync(grp.h_counts, grp.dev.req_count + 2 * grp.slot, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, grp.stream));
+            if ((rc = launch_net(pool, grp))) return rc;
+        }
+        pool->ticks++;
+        for (Group &grp : pool->groups) {
+            AZ_CUDA(cudaStreamSynchronize(grp.stream));
+            idle &= grp.h_counts[0] == 0 && grp.h_counts[1] == 0;   // no requests, nobody mid-step: every tree is done (or stalled)
+        }
+        if (idle) {
             if (idle_out) *idle_out = 1;
             break;
         }
@@ -384,26 +488,28 @@ extern "C" int az_pool_collect(az_pool *pool, float *features, int32_t *n_reques
     AZ_REQUIRE(pool && features && n_requests, AZ_ERR_ARG, "az_pool_collect: null argument");
     AZ_REQUIRE(pool->cfg.eval_mode == AZ_EVAL_EXTERNAL, AZ_ERR_STATE, "az_pool_collect: pool uses the internal net");
     AZ_REQUIRE(pool->pending_requests == 0, AZ_ERR_STATE, "az_pool_collect: previous requests not answered (az_pool_provide)");
-    cudaStream_t s = pool->ctx->stream;
+    Group &grp = pool->groups[0];               // external pools have one group
+    cudaStream_t s = grp.stream;
     *n_requests = 0;
     // The first tick consumes the evaluations handed in by az_pool_provide.  A tree may burn its step budget
     // on adjudicated leaves without reaching a leaf that needs the net, so "top-up" ticks (which leave the
     // already-waiting games alone and append to the request list) run until no tree can make progress.
     for (int attempt = 0; attempt < 65536; ++attempt) {
-        int rc = launch_tree(pool, attempt == 0);
+        int rc = launch_tree(pool, grp, attempt == 0);
         if (rc) return rc;
-        AZ_CUDA(cudaMemcpyAsync(pool->h_counts, pool->dev.req_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (attempt == 0) pool->ticks++;
+        AZ_CUDA(cudaMemcpyAsync(grp.h_counts, grp.dev.req_count + 2 * grp.slot, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         AZ_CUDA(cudaStreamSynchronize(s));
         if ((rc = check_game_errors(pool))) return rc;
         bool busy = false;
-        for (int g = 0; g < pool->dev.G; ++g) busy |= pool->h_games[g].status == ST_IDLE || pool->h_games[g].status == ST_DESCEND;
+        for (int g = 0; g < grp.dev.G; ++g) busy |= grp.h_games[g].status == ST_IDLE || grp.h_games[g].status == ST_DESCEND;
         if (!busy) break;                       // every tree is waiting, done or stalled
     }
-    const int n = pool->h_counts[0];
+    const int n = grp.h_counts[0];
     if (n > 0) {
-        aztree_launch_features(pool->dev.req_pos, n, pool->d_features, s);
+        aztree_launch_features(grp.dev.req_pos, n, grp.d_features, s);
         pool->launches++;
-        AZ_CUDA(cudaMemcpyAsync(features, pool->d_features, sizeof(float) * AZ_FEATURES * n, cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaMemcpyAsync(features, grp.d_features, sizeof(float) * AZ_FEATURES * n, cudaMemcpyDeviceToHost, s));
         AZ_CUDA(cudaStreamSynchronize(s));
     }
     AZ_CUDA(cudaGetLastError());
@@ -417,9 +523,10 @@ extern "C" int az_pool_provide(az_pool *pool, const float *logits, const float *
     AZ_REQUIRE(pool && logits && values, AZ_ERR_ARG, "az_pool_provide: null argument");
     AZ_REQUIRE(pool->pending_requests > 0, AZ_ERR_STATE, "az_pool_provide: no outstanding requests");
     const int n = pool->pending_requests;
-    cudaStream_t s = pool->ctx->stream;
-    AZ_CUDA(cudaMemcpyAsync(pool->dev.logits, logits, sizeof(float) * AZ_LOGITS * n, cudaMemcpyHostToDevice, s));
-    AZ_CUDA(cudaMemcpyAsync(pool->dev.values, values, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+    Group &grp = pool->groups[0];
+    cudaStream_t s = grp.stream;
+    AZ_CUDA(cudaMemcpyAsync(grp.dev.logits, logits, sizeof(float) * AZ_LOGITS * n, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaMemcpyAsync(grp.dev.values, values, sizeof(float) * n, cudaMemcpyHostToDevice, s));
     AZ_CUDA(cudaStreamSynchronize(s));      // the caller may free its arrays right away (complete_workload copies too)
     pool->pending_requests = 0;
     return AZ_OK;
@@ -429,13 +536,15 @@ extern "C" int az_pool_root(az_pool *pool, int game, az_position *pos, int32_t *
                             double *total_score, double *prior, int32_t *root_visits, double *root_value)
 {
     AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_root: null pool");
-    AZ_REQUIRE(game >= 0 && game < pool->dev.G, AZ_ERR_ARG, "az_pool_root: game %d out of range", game);
-    AZ_CUDA(cudaStreamSynchronize(pool->ctx->stream));
+    AZ_REQUIRE(game >= 0 && game < pool->G(), AZ_ERR_ARG, "az_pool_root: game %d out of range", game);
+    int local;
+    Group &grp = pool->group_of(game, &local);
+    AZ_CUDA(cudaStreamSynchronize(grp.stream));
     Game gm;
-    AZ_CUDA(cudaMemcpy(&gm, pool->dev.games + game, sizeof(Game), cudaMemcpyDeviceToHost));
+    AZ_CUDA(cudaMemcpy(&gm, grp.dev.games + local, sizeof(Game), cudaMemcpyDeviceToHost));
     AZ_REQUIRE(gm.status != ST_ERROR, AZ_ERR_CAPACITY, "game %d: %s", game, kErrNames[std::min(std::max(gm.error, 0), 3)]);
     std::vector<uint8_t> slot(kNodeStride);
-    AZ_CUDA(cudaMemcpy(slot.data(), pool->dev.nodes + ((size_t)game * pool->dev.C + gm.root) * kNodeStride, kNodeStride,
+    AZ_CUDA(cudaMemcpy(slot.data(), grp.dev.nodes + ((size_t)local * grp.dev.C + gm.root) * kNodeStride, kNodeStride,
                        cudaMemcpyDeviceToHost));
     const NodeHdr *h = reinterpret_cast<const NodeHdr *>(slot.data());
     if (pos) {
@@ -460,15 +569,17 @@ extern "C" int az_pool_root(az_pool *pool, int game, az_position *pos, int32_t *
 extern "C" int az_pool_play(az_pool *pool, int game, az_move move)
 {
     AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_play: null pool");
-    AZ_REQUIRE(game >= 0 && game < pool->dev.G, AZ_ERR_ARG, "az_pool_play: game %d out of range", game);
+    AZ_REQUIRE(game >= 0 && game < pool->G(), AZ_ERR_ARG, "az_pool_play: game %d out of range", game);
     AZ_REQUIRE(pool->pending_requests == 0, AZ_ERR_STATE, "az_pool_play: evaluations are outstanding");
-    cudaStream_t s = pool->ctx->stream;
-    aztree_launch_play(pool->dev, game, (int)move, pool->d_status, s);
+    int local;
+    Group &grp = pool->group_of(game, &local);
+    cudaStream_t s = grp.stream;
+    aztree_launch_play(grp.dev, local, (int)move, grp.d_status, s);
     pool->launches++;
-    AZ_CUDA(cudaMemcpyAsync(pool->h_counts + 2, pool->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(grp.h_counts + 2, grp.d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
     AZ_CUDA(cudaGetLastError());
-    const int st = pool->h_counts[2];
+    const int st = grp.h_counts[2];
     AZ_REQUIRE(st != -1, AZ_ERR_ARG, "az_pool_play: move is not legal at the root of game %d", game);
     AZ_REQUIRE(st != -2, AZ_ERR_STATE, "az_pool_play: game %d is waiting for an evaluation", game);
     AZ_REQUIRE(st == 0, AZ_ERR_CAPACITY, "az_pool_play: node pool exhausted");
@@ -476,29 +587,49 @@ extern "C" int az_pool_play(az_pool *pool, int game, az_move move)
 }
 
 namespace {
-const int kTicksPerDrain = 32;
 
-// `ticks` iterations of (tree kernel, net kernel) back to back on the stream, then one drain of finished games
+// `ticks` iterations of (tree kernel, net kernel) per group, the groups' launches interleaved on their own streams,
+// then one drain of finished games.  The first tick of every call is run with the groups serialised and is timed
+// with CUDA events (tree and net kernel each alone on the GPU): that sample feeds tree_seconds / net_seconds.
 int run_ticks(az_pool *pool, FILE *out, bool copy_records, int ticks, int64_t *games)
 {
-    cudaStream_t s = pool->ctx->stream;
     int rc = AZ_OK;
+    const size_t ng = pool->groups.size();
     for (int t = 0; t < ticks && rc == AZ_OK; ++t) {
-        const bool timed = (t == 0);            // sample the device time of one tick per drain interval
-        if (timed) cudaEventRecord(pool->ev[0], s);
-        rc = launch_tree(pool);
-        if (timed) cudaEventRecord(pool->ev[1], s);
-        if (rc == AZ_OK) rc = launch_net(pool);
-        if (timed) cudaEventRecord(pool->ev[2], s);
+        const bool timed = (t == 0);
+        if (timed && ng > 1 && (rc = sync_all(pool))) return rc;
+        for (size_t gi = 0; gi < ng && rc == AZ_OK; ++gi) {
+            Group &grp = pool->groups[gi];
+            const bool trace = !grp.trace.empty() && t < kTicksPerDrain;
+            if (timed) cudaEventRecord(grp.ev[0], grp.stream);
+            if (trace) cudaEventRecord(grp.trace[3 * t], grp.stream);
+            rc = launch_tree(pool, grp);
+            if (timed) cudaEventRecord(grp.ev[1], grp.stream);
+            if (trace) cudaEventRecord(grp.trace[3 * t + 1], grp.stream);
+            if (rc == AZ_OK) rc = launch_net(pool, grp);
+            if (timed) cudaEventRecord(grp.ev[2], grp.stream);
+            if (trace) cudaEventRecord(grp.trace[3 * t + 2], grp.stream);
+            if (timed && ng > 1 && gi == 0) AZ_CUDA(cudaStreamSynchronize(grp.stream));   // keep the sample free of overlap
+        }
+        pool->ticks++;
     }
     if (rc) return rc;
-    if ((rc = drain_finished(pool, out, games, copy_records))) return rc;
-    AZ_CUDA(cudaStreamSynchronize(s));
+    for (Group &grp : pool->groups)
+        if ((rc = drain_finished(pool, grp, out, games, copy_records))) return rc;
+    if ((rc = sync_all(pool))) return rc;
+    for (Group &grp : pool->groups)
+        for (int t = 1; t < ticks && !grp.trace.empty(); ++t) {
+            float a = 0.f, b = 0.f, c = 0.f;
+            cudaEventElapsedTime(&a, grp.trace[3 * t], grp.trace[3 * t + 1]);
+            cudaEventElapsedTime(&b, grp.trace[3 * t + 1], grp.trace[3 * t + 2]);
+            cudaEventElapsedTime(&c, grp.trace[3 * t - 1], grp.trace[3 * t]);
+            grp.trace_tree_ms += a; grp.trace_net_ms += b; grp.trace_gap_ms += c; grp.trace_n++;
+        }
     float ms_tree = 0.f, ms_net = 0.f;
-    if (cudaEventElapsedTime(&ms_tree, pool->ev[0], pool->ev[1]) == cudaSuccess &&
-        cudaEventElapsedTime(&ms_net, pool->ev[1], pool->ev[2]) == cudaSuccess) {
-        pool->tree_seconds += ms_tree * 1e-3 * ticks;       // extrapolated from the sampled tick
-        pool->net_seconds += ms_net * 1e-3 * ticks;
+    Group &g0 = pool->groups[0];
+    if (cudaEventElapsedTime(&ms_tree, g0.ev[0], g0.ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms_net, g0.ev[1], g0.ev[2]) == cudaSuccess) {
+        pool->tree_seconds += ms_tree * 1e-3 * ticks * ng;      // extrapolated from the sampled (group 0, un-overlapped) tick
+        pool->net_seconds += ms_net * 1e-3 * ticks * ng;
     }
     return AZ_OK;
 }
@@ -637,7 +768,7 @@ extern "C" int get_workload(void)
     }
     std::memcpy(g_legacy.fill[h], st.data(), sizeof(float) * AZ_FEATURES * (size_t)have);
     int64_t dummy = 0;
-    if (drain_finished(pool, g_legacy.out, &dummy)) legacy_die("drain");
+    if (drain_finished(pool, pool->groups[0], g_legacy.out, &dummy)) legacy_die("drain");
     g_legacy.waiting[h] = true;
     g_legacy.next ^= 1;
     return h;

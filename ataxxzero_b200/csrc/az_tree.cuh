@@ -85,8 +85,9 @@ struct PoolDev {
     uint32_t *gstack;        // [G][C]
     az_position *req_pos;    // [G]
     int32_t *req_game;       // [G]
-    int32_t *req_count;      // [3]: [0] requests of this tick, [1] games that still have work but made no request,
-                             //      [2] requests of the previous tick (of which the first `cap` were evaluated)
+    int32_t *req_count;      // [3 slots][2]: {requests, games that still have work but made no request} of a tick.  Ticks
+                             // rotate through the slots (tick_slot); a tick reads its predecessor's request count (of which
+                             // the first `cap` were evaluated) and zeroes its successor's slot, so the host never memsets.
     float *logits;           // [G][833]
     float *values;           // [G]
     uint32_t *records;       // [G][2][rec_cap_words]
@@ -96,6 +97,8 @@ struct PoolDev {
     int32_t levels_per_tick; // bound on tree levels a game may descend per tick (tail latency of deep endgame lines)
     int32_t cap;             // evaluations served per tick: a whole number of net-kernel rounds; later requests are re-queued
     int32_t consume;         // 1: evaluations of the previous requests are in logits/values; 0: top-up tick, leave waiting games alone
+    int32_t tick_slot;       // slot of req_count this tick appends its requests to
+    int32_t game_base;       // global index of this group's game 0 (RNG streams are keyed by the global game index)
     uint32_t rec_cap_words;
     uint64_t seed;
 };
