@@ -1,0 +1,160 @@
+"""generate_games.py of the reference (same flags and record format), with the rules batched on the GPU.
+
+``--random-play`` (BASELINE config 1, the only mode of the reference that still runs): all
+``--game-count`` games advance together -- one ``movegen`` / ``makemove`` / ``get_board_result`` kernel call per ply over
+every unfinished game -- and each is written as the reference's Python record
+``{"boards": [[49 ints]...], "moves": [[[sx,sy],[ex,ey]] | ["c",[x,y]] ...], "result": 1|2}`` (generate_games.py:20-68).
+Without ``--random-play`` the moves come from ``engine.MCTS`` (device-resident tree) as the reference intended:
+search until the most-visited root edge has ``--visit-count`` visits (at most 10x that many steps), pick a move
+proportionally to visits, and randomise the opening plies with the reference's schedule.
+"""
+import argparse
+import json
+import os
+import random
+
+from .. import Context, ataxx_rules, rules
+
+MAX_STEP_RATIO = 10
+MAXIMUM_GAME_PLIES = 400
+LOGIT_TEMPERATURE = 0.0
+OPENING_RANDOMIZATION_SCHEDULE = [0.2 * (0.5 ** (i / 2)) for i in range(10)]
+
+
+def _json_move(move):
+    return list(map(list, move)) if move[0] != "c" else ["c", list(move[1])]
+
+
+def random_play_games(ctx, count, rng=random, start_fen="x5o/7/7/7/7/7/o5x x"):
+    """`count` uniformly random games played concurrently; yields finished entries (result None is possible at 400 plies)."""
+    import numpy as np
+    start = ataxx_rules.AtaxxState.from_fen(start_fen)
+    arr = rules.positions_array([start.to_position()] * count)
+    entries = [{"boards": [], "moves": []} for _ in range(count)]
+    live = np.arange(count)
+    results = [None] * count
+    for ply in range(MAXIMUM_GAME_PLIES):
+        if len(live) == 0:
+            break
+        lists = rules.movegen_batch(ctx, arr[live])
+        picked = []
+        for g, mv in zip(live, lists):
+            st = ataxx_rules.AtaxxState.from_position(rules.array_to_positions(arr[g:g + 1])[0])
+            m = rng.choice(mv)
+            entries[g]["boards"].append(list(st.board))
+            entries[g]["moves"].append(_json_move(rules.to_reference_move(m)))
+            picked.append(m)
+        arr[live] = rules.makemove_batch(ctx, arr[live], picked)
+        res = rules.result_batch(ctx, arr[live])
+        for g, r in zip(live, res):
+            if r:
+                results[g] = int(r)
+        live = live[res == 0]
+    for g in range(count):
+        entries[g]["result"] = results[g]
+    return entries
+
+
+def mcts_game(args, engine):
+    """One self-play game driven through the engine.py interface (generate_games.py:16-77)."""
+    board = ataxx_rules.AtaxxState.initial()
+    m = engine.MCTS(board.copy(), use_dirichlet_noise=True)
+    entry = {"boards": [], "moves": []}
+    all_steps = 0
+    helper = engine.MCTSEngine.__new__(engine.MCTSEngine)       # sample_with_exponential_weight needs only .mcts
+    helper.mcts = m
+    for ply in range(MAXIMUM_GAME_PLIES):
+        while True:
+            root = m.root_node
+            most = max([e.edge_visits for e in root.outgoing_edges.values()] or [0])
+            if most >= args.visit_count or root.all_edge_visits >= args.visit_count * MAX_STEP_RATIO:
+                break
+            burst = min(64, max(1, args.visit_count - most))
+            m.search(root.all_edge_visits + burst)
+            all_steps += burst
+        training_move = selected_move = helper.sample_with_exponential_weight(1.0)
+        if ply < len(OPENING_RANDOMIZATION_SCHEDULE) and random.random() < OPENING_RANDOMIZATION_SCHEDULE[ply]:
+            selected_move = random.choice(board.legal_moves())
+        entry["boards"].append(list(board.board))
+        entry["moves"].append(_json_move(training_move))
+        m.play(board.to_move, selected_move, print_variation_count=False)
+        board.move(selected_move)
+        if board.result() is not None:
+            break
+        if args.show_game:
+            print(board)
+        if args.die_if_present and os.path.exists(args.die_if_present):
+            print("Exiting due to signal file!")
+            raise SystemExit
+    m.close()
+    entry["result"] = board.result()
+    print("[%3i] Generated a %i ply game (%.2f avg steps) with result %r." % (
+        args.group_index, len(entry["boards"]), all_steps / float(ply + 1), entry["result"]))
+    return entry
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description="Generates games in the .json format that train.py reads.",
+                                     formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument("--network", metavar="PATH", default="", help="Path of the model to load.")
+    parser.add_argument("--output-games", metavar="PATH", type=str, default=None, help="Path to write .json games to.")
+    parser.add_argument("--group-index", metavar="N", default=0, type=int, help="Our index in the work group.")
+    parser.add_argument("--use-rpc", action="store_true", help="Use RPC for NN evaluation (not supported here).")
+    parser.add_argument("--random-play", action="store_true", help="Generate games by totally random play.")
+    parser.add_argument("--visit-count", metavar="N", default=200, type=int,
+                        help="Perform MCTS steps until the PV move has at least N visits.")
+    parser.add_argument("--die-if-present", metavar="PATH", default=None, type=str, help="Die once a file is present at the target path.")
+    parser.add_argument("--show-game", action="store_true", help="Show the game while it's generating.")
+    parser.add_argument("--game-count", metavar="N", default=None, type=int, help="Maximum number of games to generate.")
+    parser.add_argument("--no-write", action="store_true", help="Don't write out generated games at all.")
+    parser.add_argument("--device", metavar="N", default=0, type=int, help="GPU index.")
+    parser.add_argument("--seed", metavar="N", default=None, type=int, help="Seed for Python's RNG (random play).")
+    return parser
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.use_rpc:
+        raise SystemExit("--use-rpc: the gevent/mprpc transport is out of scope for this package")
+    if args.seed is not None:
+        random.seed(args.seed)
+    if args.output_games is None:
+        name = os.path.splitext(os.path.basename(args.network))[0] or "random"
+        directory = os.path.join("games", name)
+        os.makedirs(directory, exist_ok=True)
+        output_path = os.path.join(directory, os.urandom(8).hex() + ".json")
+    else:
+        output_path = args.output_games
+    if args.no_write:
+        output_path = "/dev/null"
+    print("[%3i] Writing to: %s" % (args.group_index, output_path))
+    written = 0
+    with open(output_path, "w") as f:          # "w", as the reference does despite its help text (generate_games.py:127)
+        def emit(entry):
+            nonlocal written
+            if entry["result"] is None:
+                print("[%3i] Skipping game with null result." % (args.group_index,))
+                return
+            json.dump(entry, f)
+            f.write("\n")
+            f.flush()
+            written += 1
+        if args.random_play:
+            print("Doing random play! Loading no model, and not using RPC.")
+            with Context(device=args.device) as ctx:
+                target = args.game_count if args.game_count is not None else 1 << 62
+                while written < target:
+                    for entry in random_play_games(ctx, min(4096, target - written)):
+                        emit(entry)
+        else:
+            from .. import engine
+            engine.setup_evaluator(use_rpc=False, temperature=LOGIT_TEMPERATURE)
+            engine.initialize_model(args.network, device=args.device)
+            while args.game_count is None or written < args.game_count:
+                emit(mcts_game(args, engine))
+    print("Done generating games.")
+    return written
+
+
+if __name__ == "__main__":
+    main()

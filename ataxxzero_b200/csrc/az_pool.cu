@@ -566,6 +566,35 @@ extern "C" int az_pool_root(az_pool *pool, int game, az_position *pos, int32_t *
     return AZ_OK;
 }
 
+extern "C" int az_pool_pv(az_pool *pool, int game, az_move *moves, int32_t *visits, int max_len, int32_t *len_out)
+{
+    AZ_REQUIRE(pool && moves && len_out && max_len >= 0, AZ_ERR_ARG, "az_pool_pv: bad argument");
+    AZ_REQUIRE(game >= 0 && game < pool->G(), AZ_ERR_ARG, "az_pool_pv: game %d out of range", game);
+    int local;
+    Group &grp = pool->group_of(game, &local);
+    AZ_CUDA(cudaStreamSynchronize(grp.stream));
+    Game gm;
+    AZ_CUDA(cudaMemcpy(&gm, grp.dev.games + local, sizeof(Game), cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> slot(kNodeStride);
+    int node = gm.root, n = 0;
+    while (n < max_len && node >= 0) {                      // select_principal_variation(best=True), engine.py:331-336
+        AZ_CUDA(cudaMemcpy(slot.data(), grp.dev.nodes + ((size_t)local * grp.dev.C + node) * kNodeStride, kNodeStride, cudaMemcpyDeviceToHost));
+        const NodeHdr *h = reinterpret_cast<const NodeHdr *>(slot.data());
+        const uint32_t *nv = reinterpret_cast<const uint32_t *>(slot.data() + kOffN);
+        const int32_t *ch = reinterpret_cast<const int32_t *>(slot.data() + kOffChild);
+        int best = -1;
+        for (int i = 0; i < h->n_moves; ++i)
+            if (ch[i] >= 0 && (best < 0 || nv[i] > nv[best])) best = i;      // max(): first of the most visited edges
+        if (best < 0) break;
+        moves[n] = reinterpret_cast<const uint16_t *>(slot.data() + kOffMove)[best];
+        if (visits) visits[n] = (int32_t)nv[best];
+        ++n;
+        node = ch[best];
+    }
+    *len_out = n;
+    return AZ_OK;
+}
+
 extern "C" int az_pool_play(az_pool *pool, int game, az_move move)
 {
     AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_play: null pool");

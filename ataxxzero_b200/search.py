@@ -46,6 +46,7 @@ _native.register("az_pool_provide", C.c_int, [_vp, _vp, _vp])
 _native.register("az_pool_root", C.c_int, [_vp, C.c_int, C.POINTER(Position), C.POINTER(C.c_int32), _vp, _vp, _vp, _vp,
                                            C.POINTER(C.c_int32), C.POINTER(C.c_double)])
 _native.register("az_pool_play", C.c_int, [_vp, C.c_int, C.c_uint16])
+_native.register("az_pool_pv", C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.POINTER(C.c_int32)])
 _native.register("az_selfplay_run", C.c_int, [_vp, C.c_char_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(PoolStats)])
 _native.register("az_selfplay_ticks", C.c_int, [_vp, C.c_char_p, C.c_int64, C.POINTER(PoolStats)])
 
@@ -145,6 +146,15 @@ class Pool:
         k = n.value
         return {"position": pos, "moves": [unpack_move(m) for m in moves[:k]], "visits": visits[:k].tolist(),
                 "total_score": total[:k].copy(), "prior": prior[:k].copy(), "root_visits": rv.value, "value": val.value}
+
+    def principal_variation(self, game=0, max_len=64):
+        """Most-visited line below the root: [(move, edge_visits), ...] (engine.py:331-336, best=True)."""
+        moves = np.zeros(max_len, dtype=np.uint16)
+        visits = np.zeros(max_len, dtype=np.int32)
+        n = C.c_int32()
+        check(lib().az_pool_pv(self._h, int(game), C.c_void_p(moves.ctypes.data), C.c_void_p(visits.ctypes.data), int(max_len),
+                               C.byref(n)))
+        return [(unpack_move(m), int(v)) for m, v in zip(moves[:n.value], visits[:n.value])]
 
     def play(self, game, move):
         """MCTS::play (self_play_client.cpp:475-492)."""

@@ -173,6 +173,8 @@ int az_pool_provide(az_pool *pool, const float *logits, const float *values);
 /* root statistics in reference movegen order (visits[i] = edge_visits or 0 when no edge exists) */
 int az_pool_root(az_pool *pool, int game, az_position *pos, int32_t *n_moves, az_move *moves, int32_t *visits,
                  double *total_score, double *prior, int32_t *root_visits, double *root_value);
+/* engine.py:331-336 select_principal_variation(best=True): the most-visited line below the root, at most max_len plies */
+int az_pool_pv(az_pool *pool, int game, az_move *moves, int32_t *visits, int max_len, int32_t *len_out);
 /* MCTS::play(move) (self_play_client.cpp:475-492): re-root on the child (subtree kept) or rebuild */
 int az_pool_play(az_pool *pool, int game, az_move move);
 

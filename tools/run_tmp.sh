@@ -1,5 +1,1 @@
-export AZ_POOL_TRACE=1
-AZ_POOL_GROUPS=2 AZ_POOL_NET_TILES=2 AZ_NET_MAX_CTAS=128 python tools/tick_timing.py 2048 800 512
-AZ_POOL_GROUPS=2 AZ_POOL_NET_TILES=2 AZ_NET_MAX_CTAS=100 python tools/tick_timing.py 2048 800 512
-AZ_POOL_GROUPS=2 AZ_POOL_NET_TILES=2 AZ_LEVELS_PER_TICK=24 python tools/tick_timing.py 2048 800 512
-AZ_POOL_GROUPS=2 AZ_POOL_NET_TILES=2 AZ_LEVELS_PER_TICK=16 python tools/tick_timing.py 2048 800 512
+python -m pytest tests/test_cli_gpu.py -x -q 2>&1 | tail -30
