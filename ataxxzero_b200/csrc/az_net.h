@@ -5,6 +5,9 @@
 
 constexpr int AZ_F = 128;            // filters (model.py:16)
 constexpr float AZ_BN_EPS = 1e-3f;
+#ifndef AZ_NET_CLUSTER_DEFAULT
+#define AZ_NET_CLUSTER_DEFAULT 2
+#endif
 #ifndef AZ_NET_TILES_DEFAULT
 #define AZ_NET_TILES_DEFAULT 1
 #endif   // tf.layers.batch_normalization default epsilon
@@ -26,6 +29,7 @@ struct AzNet {
     // bf16 tensor-core mode (az_net_tc.cu): BN scale folded into the weights, UMMA operand layout
     uint8_t *tc_stream = nullptr;      // [input conv | tower | heads] in the order the TMA producer streams them
     int tc_tiles = 2;                  // kernel variant: tiles (of 2 boards) per CTA
+    int tc_cluster = 1;                // CTAs per cluster sharing one multicast weight stream
     __nv_bfloat16 *tc_w = nullptr;     // [2*blocks][18 chunks][8 kgroups][128 cout][8 cin]
     float *tc_shift = nullptr;         // [layers][F]   -mean * scale
     __nv_bfloat16 *tc_w_in = nullptr;  // [5 k-steps][2 k-groups = taps][128 cout][8 cin (4 real)] bf16, scale folded

@@ -114,6 +114,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// the same copy, delivered to the same shared-memory offset (and signalling the same mbarrier offset) of every CTA in
+// `cta_mask` of the cluster: one L2 read feeds several SMs
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t cta_mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -178,6 +197,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// arrive on the barrier at this offset in every CTA of `cta_mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
+                 : "memory");
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
@@ -234,6 +259,7 @@ struct TcParams {
     float *logits;                     // [n][833]
     float *values;                     // [n]
     float *debug_act;                  // [n][49][128] (debug only)
+    int experiment;                    // AZ_NET_EXPERIMENT bits: 1 = no weight copies (stale smem), 2 = no tower MMAs.  Wrong results; timing studies only.
 };
 
 // row r of a tile -> board within tile / cell; real rows carry data, the rest are zero padding
@@ -246,10 +272,16 @@ __device__ __forceinline__ bool row_is_real(int r, int &board_in_tile, int &cell
     return w >= 8 && y != 7;
 }
 
-template <int TILES, int IN_KIND>
+// CS = thread-block cluster size.  The CS CTAs of a cluster walk the same weight stream in lockstep: each fetches 1/CS of
+// every pipeline stage from L2 and multicasts it into the shared memory of all of them, so the L2 -> SM weight traffic
+// (the kernel's real bottleneck: ~12 TB/s without it) drops by CS.  A stage slot is free once the MMA issuers of ALL the
+// cluster's CTAs have committed it (empty barriers count CS multicast arrivals).
+template <int TILES, int IN_KIND, int CS>
 __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_SM) k_net_tc(const TcParams P)
 {
     using C = Cfg<TILES>;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CS) - 1);
+    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -258,7 +290,7 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
     constexpr int B_FULL = 0, B_EMPTY = STAGES, B_ACC = 2 * STAGES, B_ACT = 2 * STAGES + TILES, B_IN = 2 * STAGES + 2 * TILES;
 
     const int n_boards = P.n_ptr ? min(*P.n_ptr, P.n) : P.n;
-    const int num_units = (n_boards + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS;
+    const int num_units = ((n_boards + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS + CS - 1) / CS * CS;   // cluster peers run the same number of passes
     const int tower_layers = P.layers - 1;          // tensor-core 128->128 convs
     const int run_layers = P.debug_layers >= 0 ? min(P.debug_layers, P.layers) : P.layers;   // conv layers executed (incl. input conv)
     const int nl = min(tower_layers, run_layers - 1);
@@ -269,7 +301,7 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
     for (int i = threadIdx.x; i < (C::IN_BYTES + ZERO_BYTES) / 16; i += C::NUM_THREADS)
         reinterpret_cast<uint4 *>(smem + C::OFF_IN)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), CS); }
         for (int t = 0; t < TILES; ++t) { mbar_init(bar(B_ACC + t), 1); mbar_init(bar(B_ACT + t), 128); }
         mbar_init(bar(B_IN), 128 * TILES);
         fence_barrier_init();
@@ -278,6 +310,7 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
     fence_proxy_async();                 // zero-fills above must be visible to the tensor core's async proxy
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();      // every peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + C::OFF_TMEM);
 
@@ -289,8 +322,14 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
             auto push = [&](const uint8_t *src, uint32_t bytes) {
                 const int s = it % STAGES;
                 mbar_wait(bar(B_EMPTY + s), ((it / STAGES) & 1) ^ 1);
-                mbar_expect_tx(bar(B_FULL + s), bytes);
-                bulk_g2s(sbase + C::OFF_RING + s * STAGE_BYTES, src, bytes, bar(B_FULL + s));
+                if (P.experiment & 1) { mbar_arrive(bar(B_FULL + s)); ++it; return; }
+                mbar_expect_tx(bar(B_FULL + s), bytes);           // the whole stage: own slice + the peers' slices
+                if (CS == 1) {
+                    bulk_g2s(sbase + C::OFF_RING + s * STAGE_BYTES, src, bytes, bar(B_FULL + s));
+                } else {
+                    const uint32_t slice = bytes / CS;
+                    bulk_g2s_multicast(sbase + C::OFF_RING + s * STAGE_BYTES + crank * slice, src + crank * slice, slice, bar(B_FULL + s), CMASK);
+                }
                 ++it;
             };
             const uint8_t *tower = P.w_stream + WIN_BYTES;
@@ -315,7 +354,11 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                 tc_fence_after();
                 return sbase + C::OFF_RING + s * STAGE_BYTES;
             };
-            auto release = [&]() { umma_commit(bar(B_EMPTY + it % STAGES)); ++it; };
+            auto free_stage = [&](int s) {
+                if (CS == 1) umma_commit(bar(B_EMPTY + s));
+                else umma_commit_multicast(bar(B_EMPTY + s), CMASK);
+            };
+            auto release = [&]() { free_stage(it % STAGES); ++it; };
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
                 // ---- input conv: 9 taps x 8 (4 real) channels, two taps per K=16 step ----
                 mbar_wait(bar(B_IN), in_phase);
@@ -365,10 +408,11 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                                 const uint32_t a_lo = a_lo0 + t * TILE_M + half * A_HALF + (uint32_t)((tap / 3 - 1) * 8 + (tap % 3 - 1));
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
+                                    if (!(P.experiment & 2) || (half | tap | j) == 0)
                                     umma_lo(d_col + t * 128, a_lo + j * A_KSTEP, a_hi, b_lo + j * B_KSTEP, b_hi, IDESC_128,
                                             onto_res | (uint32_t)((half | tap | j) != 0));
                                 if (half == 1 && tap == 8) umma_commit(bar(B_ACC + t));
-                                umma_commit(bar(B_EMPTY + s));
+                                free_stage(s);
                                 ++it;
                             }
                         }
@@ -506,6 +550,7 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();      // no CTA leaves while a peer may still multicast into it
     if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
@@ -573,10 +618,13 @@ int az_net_tc_alloc(AzNet *net)
     net->tc_w = reinterpret_cast<__nv_bfloat16 *>(net->tc_stream + WIN_BYTES);
     net->tc_w_heads = reinterpret_cast<__nv_bfloat16 *>(net->tc_stream + WIN_BYTES + tower);
     AZ_CUDA(cudaMalloc(&net->tc_shift, (size_t)net->layers * F * 4));
-    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<1, AZ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
-    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<1, AZ_IN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
-    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<2, AZ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
-    AZ_CUDA(cudaFuncSetAttribute(k_net_tc<2, AZ_IN_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::SMEM_BYTES));
+#define AZ_TC_ATTR(T, K, CSZ) AZ_CUDA(cudaFuncSetAttribute(k_net_tc<T, K, CSZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<T>::SMEM_BYTES))
+    AZ_TC_ATTR(1, AZ_IN_F32, 1); AZ_TC_ATTR(1, AZ_IN_POS, 1); AZ_TC_ATTR(2, AZ_IN_F32, 1); AZ_TC_ATTR(2, AZ_IN_POS, 1);
+    AZ_TC_ATTR(1, AZ_IN_F32, 2); AZ_TC_ATTR(1, AZ_IN_POS, 2); AZ_TC_ATTR(2, AZ_IN_F32, 2); AZ_TC_ATTR(2, AZ_IN_POS, 2);
+    AZ_TC_ATTR(1, AZ_IN_F32, 4); AZ_TC_ATTR(1, AZ_IN_POS, 4); AZ_TC_ATTR(2, AZ_IN_F32, 4); AZ_TC_ATTR(2, AZ_IN_POS, 4);
+#undef AZ_TC_ATTR
+    const char *cenv = getenv("AZ_NET_CLUSTER");       // CTAs sharing one weight stream by multicast: 1, 2 or 4
+    net->tc_cluster = cenv ? (atoi(cenv) == 4 ? 4 : atoi(cenv) == 2 ? 2 : 1) : AZ_NET_CLUSTER_DEFAULT;
     const char *env = getenv("AZ_NET_TILES");          // tuning knob: 1 = two single-tile CTAs per SM, 2 = one two-tile CTA per SM
     net->tc_tiles = (env && atoi(env) == 2) ? 2 : (env && atoi(env) == 1) ? 1 : AZ_NET_TILES_DEFAULT;
     return AZ_OK;
@@ -603,18 +651,44 @@ void az_net_tc_release(AzNet *net)
     net->tc_shift = nullptr;
 }
 
+template <int TILES, int CS>
+static cudaError_t tc_launch_cluster(const TcParams &P, int in_kind, int grid, cudaStream_t stream)
+{
+    using C = Cfg<TILES>;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(C::NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (in_kind == AZ_IN_F32) return cudaLaunchKernelEx(&cfg, k_net_tc<TILES, AZ_IN_F32, CS>, P);
+    return cudaLaunchKernelEx(&cfg, k_net_tc<TILES, AZ_IN_POS, CS>, P);
+}
+
 template <int TILES>
-static void tc_launch_variant(az_context *ctx, const TcParams &P, int in_kind, int n, cudaStream_t stream)
+static void tc_launch_variant(az_context *ctx, const TcParams &P, int in_kind, int n, cudaStream_t stream, int cluster)
 {
     using C = Cfg<TILES>;
     const int units = (n + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS;
     int slots = ctx->sm_count * C::CTAS_PER_SM;
     if (const char *env = getenv("AZ_NET_MAX_CTAS")) slots = std::max(1, std::min(slots, atoi(env)));     // experiment knob
-    const int grid = units < slots ? units : slots;
+    int grid = units < slots ? units : slots;
+    if (cluster > 1) {
+        grid = (grid + cluster - 1) / cluster * cluster;          // whole clusters; surplus CTAs run an all-padding pass
+        if (cluster == 2) tc_launch_cluster<TILES, 2>(P, in_kind, grid, stream);
+        else tc_launch_cluster<TILES, 4>(P, in_kind, grid, stream);
+        return;
+    }
     if (in_kind == AZ_IN_F32)
-        k_net_tc<TILES, AZ_IN_F32><<<grid, C::NUM_THREADS, C::SMEM_BYTES, stream>>>(P);
+        k_net_tc<TILES, AZ_IN_F32, 1><<<grid, C::NUM_THREADS, C::SMEM_BYTES, stream>>>(P);
     else
-        k_net_tc<TILES, AZ_IN_POS><<<grid, C::NUM_THREADS, C::SMEM_BYTES, stream>>>(P);
+        k_net_tc<TILES, AZ_IN_POS, 1><<<grid, C::NUM_THREADS, C::SMEM_BYTES, stream>>>(P);
 }
 
 int az_net_tc_boards_per_round(az_context *ctx, int tiles)
@@ -643,8 +717,10 @@ static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind,
     P.logits = d_logits;
     P.values = d_values;
     P.debug_act = d_debug;
-    if (tiles == 1) tc_launch_variant<1>(ctx, P, in_kind, n, stream);
-    else tc_launch_variant<2>(ctx, P, in_kind, n, stream);
+    static const int experiment = getenv("AZ_NET_EXPERIMENT") ? atoi(getenv("AZ_NET_EXPERIMENT")) : 0;
+    P.experiment = experiment;
+    if (tiles == 1) tc_launch_variant<1>(ctx, P, in_kind, n, stream, net->tc_cluster);
+    else tc_launch_variant<2>(ctx, P, in_kind, n, stream, net->tc_cluster);
     ctx->launches++;
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;

@@ -345,6 +345,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         } else {
             grp.stream = ctx->stream;
         }
+        if (getenv("AZ_POOL_PROFILE")) rc |= dev_alloc(&D.prof, G * 8);
         if (getenv("AZ_POOL_TRACE")) {
             grp.trace.resize(3 * kTicksPerDrain);
             for (auto &e : grp.trace) cudaEventCreate(&e);
@@ -366,6 +367,20 @@ extern "C" void az_pool_destroy(az_pool *pool)
     cudaStreamSynchronize(pool->ctx->stream);
     for (Group &grp : pool->groups) {
         if (grp.stream) cudaStreamSynchronize(grp.stream);
+        if (grp.dev.prof) {              // per-phase cycles, accumulated over every tick: mean and worst game
+            std::vector<unsigned long long> h((size_t)grp.dev.G * 8);
+            cudaMemcpy(h.data(), grp.dev.prof, h.size() * 8, cudaMemcpyDeviceToHost);
+            const char *names[6] = {"populate", "backup", "descent", "expand", "make_move", "total"};
+            for (int ph = 0; ph < 6; ++ph) {
+                double sum = 0, mx = 0;
+                for (int g = 0; g < grp.dev.G; ++g) { sum += (double)h[(size_t)g * 8 + ph]; mx = std::max(mx, (double)h[(size_t)g * 8 + ph]); }
+                fprintf(stderr, "[az_pool profile] %-9s mean %.1f kcycles/tick/game, worst game %.1f kcycles/tick (%llu ticks)\n", names[ph],
+                        sum / grp.dev.G / std::max<uint64_t>(pool->ticks, 1) / 1e3, mx / std::max<uint64_t>(pool->ticks, 1) / 1e3,
+                        (unsigned long long)pool->ticks);
+            }
+            cudaFree(grp.dev.prof);
+            grp.dev.prof = nullptr;
+        }
         if (grp.trace_n)
             fprintf(stderr, "[az_pool trace] group@%d: tree %.3f ms, net %.3f ms (launch to completion, overlapped), idle gap %.3f ms, %llu ticks\n",
                     grp.first_game, grp.trace_tree_ms / grp.trace_n, grp.trace_net_ms / grp.trace_n, grp.trace_gap_ms / grp.trace_n,

@@ -34,7 +34,7 @@ METRIC = "selfplay_positions_per_sec"
 UNIT = "positions/s"
 GAMES_PER_GPU = 2048
 VISITS = 800
-TICKS_PER_STEP = 256
+TICKS_PER_STEP = 1024
 FLOP_PER_EVAL = 347.49e6          # dense FLOPs of one forward pass
 
 
@@ -108,7 +108,9 @@ class ReferencePipeline:
     def __init__(self, visits, buffer_size=128):
         import ctypes
         import numpy as np
+        import torch
         from oracle import cpu as ocpu, net_numpy, net_torch
+        torch.set_num_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every core
         self.np, self.ctypes = np, ctypes
         self.kind = "reference" if os.path.exists(ocpu.REF_CLIENT_SO) else "port"
         self.visits, self.B = visits, buffer_size
@@ -265,13 +267,12 @@ def run_ours(args):
     import ataxxzero_b200 as az
     from ataxxzero_b200 import model, net, rules, search
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from ataxxzero_b200 import dist as azdist
+    rank, local_rank, world = azdist.env_rank()
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        azdist.init("nccl")                   # counters only: the games themselves never cross ranks
 
     def barrier():
         if world > 1:
@@ -285,7 +286,7 @@ def run_ours(args):
 
     k, w = max(args.steps, 1), max(args.warmup, 3)
     games, visits, ticks = args.games, args.visits, args.ticks_per_step
-    ctx = az.Context(device=local_rank, seed=1000 + rank)
+    ctx = az.Context(device=local_rank, seed=azdist.rank_seed(1000, rank))
     network = model.Network.random_init(seed=0)          # "model-001": the reference's init distributions
     packed = network.packed()
     net.load_weights(ctx, network)
@@ -325,15 +326,21 @@ def run_ours(args):
     net_s = max(d["net_seconds"], 1e-9)
     achieved = d["evals"] * FLOP_PER_EVAL / net_s / 1e12
     peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)))
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_net_tc"]["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "kernel": "k_net_tc (bf16 tcgen05 tower)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write per launch from profiles/ (ncu --set full); the weights stream from L2",
+                "flop_per_launch": d["evals"] / max(d["ticks"], 1) * FLOP_PER_EVAL,
                 "peak_kind": "%s bf16_tflops_sustained (kernel timed inside a long step)" % pk_kind,
                 "net_share_of_step": d["net_seconds"] / max(d["net_seconds"] + d["tree_seconds"], 1e-9),
                 "tree_ms_per_tick": d["tree_seconds"] / max(d["ticks"], 1) * 1e3,
                 "net_ms_per_tick": d["net_seconds"] / max(d["ticks"], 1) * 1e3}
 
     # ---- end to end: host weights in, JSON game records out, every step ----
-    out_path = os.path.join(tempfile.gettempdir(), "az_bench_rank%d.json" % rank)
+    out_path = azdist.rank_output_path(os.path.join(tempfile.gettempdir(), "az_bench_model-001.json"), rank, max(world, 2))
     if os.path.exists(out_path):
         os.unlink(out_path)
     barrier()
@@ -358,6 +365,34 @@ def run_ours(args):
            "d2h_bytes_per_step": int(record_bytes / k), "json_bytes_per_step": int(json_bytes / k),
            "api": "net.load_weights + Pool.selfplay_ticks(ticks, path) -> az_net_load / az_selfplay_ticks"}
 
+    # ---- BASELINE configs[4]: single-tree search (replicas only, rank 0) + leaf-batch latency of the net kernel ----
+    single = {}
+    if rank == 0 and not args.no_single_tree:
+        golden = os.path.join(ROOT, "tests", "golden", "mcts_golden.json")
+        fen = json.load(open(golden))["midgame_fen"] if os.path.exists(golden) else rules.START_FEN
+        with search.Pool(ctx, 1, 64, eval_mode=search.EVAL_BF16, node_capacity=args.single_tree_visits + 64, steps_per_tick=64) as tree:
+            tree.set_root(0, rules.set_board(fen))
+            tree.run()                                   # warm-up: 64 visits
+            tree.set_visits(args.single_tree_visits)
+            t0 = time.perf_counter()
+            tree.run()
+            dt = time.perf_counter() - t0
+            st = tree.stats()
+            single = {"fen": fen, "visits": args.single_tree_visits, "visits_per_s": (args.single_tree_visits - 64) / dt,
+                      "mode": "bit-exact sequential PUCT (one leaf per tick, no virtual loss)", "ticks": st["ticks"]}
+        lat = {}
+        feats = np.zeros((128, 7, 7, 4), dtype=np.float32)
+        feats[..., 0] = 1.0
+        for b in (1, 8, 32, 128):
+            samples = []
+            for _ in range(30):
+                t0 = time.perf_counter()
+                net.forward(ctx, feats[:b], net.BF16)
+                samples.append((time.perf_counter() - t0) * 1e6)
+            samples.sort()
+            lat["batch%d" % b] = {"p50_us": samples[len(samples) // 2], "p99_us": samples[-1]}
+        single["leaf_batch_latency_host_to_host"] = lat
+
     # ---- secondary metric of BASELINE.json: perft Mnodes/s (device time incl. frontier expansion) ----
     perft = {}
     for depth in (7, 8):
@@ -379,7 +414,8 @@ def run_ours(args):
                        "parallelism": "games sharded across ranks, no data-path collective"},
             "e2e": e2e, "roofline": roofline, "clocks": clocks, "gpu_launches": int(d["kernel_launches"]),
             "extra": {"leaf_evals_per_s": evals / (ms * 1e-3), "mcts_steps_per_s": steps / (ms * 1e-3),
-                      "evals_per_position": evals / max(positions, 1), "max_depth": s1["max_depth"], "perft": perft}}
+                      "evals_per_position": evals / max(positions, 1), "max_depth": s1["max_depth"], "perft": perft,
+                      "single_tree": single}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pool.close()
         try:
@@ -404,6 +440,8 @@ def main():
     ap.add_argument("--ticks-per-step", type=int, default=TICKS_PER_STEP)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-tree", action="store_true")
+    ap.add_argument("--single-tree-visits", type=int, default=4000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
