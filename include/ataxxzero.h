@@ -188,6 +188,22 @@ int az_selfplay_run(az_pool *pool, const char *output_path, int64_t target_games
  * output_path = NULL finished games are recycled on the device and their records are not copied out. */
 int az_selfplay_ticks(az_pool *pool, const char *output_path, int64_t ticks, az_pool_stats *stats_out);
 
+/* ---------------- training-sample extraction (train.py:43-77 get_sample_from_entries) ---------------- */
+/* A minibatch of (features, policy target, value target) triples straight from ply records.
+ *   plies:   table of ply records, uint32 words each: [0,1] x bitboard, [2,3] o bitboard, [4] played move | entries<<16,
+ *            [5] N = sum of visit counts (0: pair values are float32 probabilities), then `entries` pairs (move, count|prob)
+ *            -- the binary layout the self-play kernels record, or the same packed from JSON game files;
+ *   offsets: word offset of each sample's ply record;   meta: bit 0 side to move (0 = x), bits 1-2 game result (1|2),
+ *            bits 3-5 dihedral symmetry index (train.py:11-23), bit 6: 1 = use the visit distribution ("dists"),
+ *            0 = one-hot on the played move (records without "dists", train.py:62-63).
+ * Outputs: features int8 [n][7][7][4] (engine.board_to_features; plane 3 is 0), policy float32
+ * [n][7][7][17], value float32 [n] (+1 when the side to move won, else -1). */
+int az_samples_extract(az_context *ctx, const uint32_t *plies, size_t ply_words, const uint64_t *offsets, const uint32_t *meta, int n,
+                       int8_t *features, float *policy, float *value);
+/* device-resident variant (all pointers on the context's GPU; runs on the context stream, no sync, no validation) */
+int az_samples_extract_dev(az_context *ctx, const void *d_plies, const void *d_offsets, const void *d_meta, int n, void *d_features,
+                           void *d_policy, void *d_value);
+
 /* ---------------- legacy 4-function ABI (link.py:8-32; self_play_client.cpp:683,708,723,740) -------- */
 /* Same names, arguments and blocking behaviour.  The trees live on GPU 0 (or $AZ_DEVICE); the caller is
  * the evaluator: get_workload() fills fill_buffer{1,2} with `buffer_entries` feature planes and returns the
