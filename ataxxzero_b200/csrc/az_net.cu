@@ -303,6 +303,75 @@ extern "C" int az_net_forward(az_context *ctx, const float *features, int n, int
     return AZ_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// symmetry-ensembled evaluation (nn_evals.py:48-62): the 8 dihedral images of a position go through the net as one
+// batch; the policies are rotated back SPATIALLY only (the reference does not permute the 16 direction planes,
+// SURVEY App. B-9 -- kept) and averaged, the values are averaged.
+// ---------------------------------------------------------------------------------------------
+namespace {
+// nn_evals.apply_symmetry (:7-15): out[i][j] = in[a'][b'] with (a, b) = sym&4 ? (j, i) : (i, j), b' = sym&2 ? 6-b : b, a' = sym&1 ? 6-a : a
+__device__ __forceinline__ int sym_source_cell(int sym, int i, int j)
+{
+    int a = (sym & 4) ? j : i, b = (sym & 4) ? i : j;
+    if (sym & 2) b = 6 - b;
+    if (sym & 1) a = 6 - a;
+    return a * 7 + b;
+}
+__constant__ int kInverseSymmetry[8] = {0, 1, 2, 3, 4, 6, 5, 7};      // nn_evals.py:27
+
+__global__ void k_sym8_expand(const float4 *__restrict__ in, int n, float4 *__restrict__ out)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;            // (board, sym, cell)
+    if (idx >= n * 8 * 49) return;
+    const int cell = idx % 49, sym = (idx / 49) & 7, b = idx / (49 * 8);
+    out[idx] = in[b * 49 + sym_source_cell(sym, cell / 7, cell % 7)];
+}
+
+__global__ void k_sym8_reduce(const float *__restrict__ logits8, const float *__restrict__ values8, int n, float *__restrict__ logits,
+                              float *__restrict__ values)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;            // (board, cell, plane)
+    if (idx < n * AZ_LOGITS) {
+        const int b = idx / AZ_LOGITS, r = idx % AZ_LOGITS, cell = r / 17, plane = r % 17;
+        float acc = 0.f;
+        for (int sym = 0; sym < 8; ++sym) {                           // np.mean(axis=0): images added in order, then / 8
+            const int src = sym_source_cell(kInverseSymmetry[sym], cell / 7, cell % 7);
+            const float v = logits8[((size_t)(b * 8 + sym) * 49 + src) * 17 + plane];
+            acc = sym ? acc + v : v;
+        }
+        logits[idx] = acc * 0.125f;
+    }
+    if (idx < n) {
+        const float *v = values8 + (size_t)idx * 8;                   // np.mean of 8 floats: numpy's pairwise tree
+        values[idx] = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) * 0.125f;
+    }
+}
+}  // namespace
+
+extern "C" int az_net_forward_sym8(az_context *ctx, const float *features, int n, int mode, float *logits, float *values)
+{
+    AZ_REQUIRE(ctx && n >= 0 && (n == 0 || (features && logits && values)), AZ_ERR_ARG, "az_net_forward_sym8: bad argument");
+    AZ_REQUIRE(ctx->net, AZ_ERR_STATE, "az_net_forward_sym8: no weights loaded (call az_net_load first)");
+    if (n == 0) return AZ_OK;
+    const size_t nn = (size_t)n, fb = sizeof(float) * AZ_FEATURES * nn, lb = sizeof(float) * AZ_LOGITS * nn;
+    AzBuffer *b = ctx->scratch;
+    AZ_REQUIRE(b[0].reserve(fb) == 0 && b[1].reserve(8 * fb) == 0 && b[2].reserve(8 * lb) == 0 && b[3].reserve(8 * 4 * nn) == 0 &&
+                   b[4].reserve(lb) == 0 && b[5].reserve(4 * nn) == 0,
+               AZ_ERR_CUDA, "az_net_forward_sym8: device scratch alloc");
+    cudaStream_t s = ctx->stream;
+    AZ_CUDA(cudaMemcpyAsync(b[0].ptr, features, fb, cudaMemcpyHostToDevice, s));
+    k_sym8_expand<<<(n * 8 * 49 + 255) / 256, 256, 0, s>>>(b[0].as<float4>(), n, b[1].as<float4>());
+    int rc = net_forward_dev(ctx, b[1].ptr, AZ_IN_F32, 8 * n, mode, b[2].ptr, b[3].ptr);
+    if (rc) return rc;
+    k_sym8_reduce<<<(n * AZ_LOGITS + 255) / 256, 256, 0, s>>>(b[2].as<float>(), b[3].as<float>(), n, b[4].as<float>(), b[5].as<float>());
+    ctx->launches += 2;
+    AZ_CUDA(cudaMemcpyAsync(logits, b[4].ptr, lb, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(values, b[5].ptr, 4 * nn, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
 extern "C" int az_net_forward_i8(az_context *ctx, const int8_t *features, int n, int mode, float *logits, float *values)
 {
     AZ_REQUIRE(ctx && n >= 0 && (n == 0 || (features && logits && values)), AZ_ERR_ARG, "az_net_forward_i8: bad argument");

@@ -18,6 +18,7 @@ _native.register("az_net_load", C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int
 _native.register("az_net_param_count", C.c_size_t, [C.c_int, C.c_int])
 _native.register("az_net_forward", C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp])
 _native.register("az_net_forward_i8", C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp])
+_native.register("az_net_forward_sym8", C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp])
 _native.register("az_net_forward_dev", C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp])
 _native.register("az_net_forward_pos_dev", C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp])
 
@@ -52,6 +53,32 @@ def forward(ctx, features, mode=BF16):
     else:
         feats = np.ascontiguousarray(feats, dtype=np.float32)
         check(lib().az_net_forward(ctx.handle, _ptr(feats), n, mode, _ptr(logits), _ptr(values)))
+    return logits[:n], values[:n]
+
+
+def apply_symmetry(tensor, symmetry):
+    """nn_evals.py:7-15."""
+    assert 0 <= symmetry < 8
+    if symmetry & 1:
+        tensor = tensor[::-1, :]
+    if symmetry & 2:
+        tensor = tensor[:, ::-1]
+    if symmetry & 4:
+        tensor = np.moveaxis(tensor, 0, 1)
+    return tensor
+
+
+inverse_symmetry = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4, 5: 6, 6: 5, 7: 7}      # nn_evals.py:27
+
+
+def evaluate_symmetric(ctx, features, mode=BF16):
+    """nn_evals.evaluate (nn_evals.py:48-62) for a batch: features [B,7,7,4] -> (mean policy [B,7,7,17], mean value [B])
+    over the 8 dihedral images of every position, expanded / reduced on the GPU (az_net_forward_sym8)."""
+    feats = np.ascontiguousarray(features, dtype=np.float32).reshape(-1, 7, 7, 4)
+    n = len(feats)
+    logits = np.zeros((max(n, 1), 7, 7, 17), dtype=np.float32)
+    values = np.zeros(max(n, 1), dtype=np.float32)
+    check(lib().az_net_forward_sym8(ctx.handle, _ptr(feats), n, mode, _ptr(logits), _ptr(values)))
     return logits[:n], values[:n]
 
 

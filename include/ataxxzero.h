@@ -111,6 +111,9 @@ size_t az_net_param_count(int filters, int blocks);   /* expected `count` */
 int az_net_forward(az_context *ctx, const float *features, int n, int mode, float *logits, float *values);
 /* gpu_server.py:52-56 wire form: int8 features [n][196] (rpc_client.py:16-19) */
 int az_net_forward_i8(az_context *ctx, const int8_t *features, int n, int mode, float *logits, float *values);
+/* nn_evals.py:48-62 evaluate(board): mean policy (rotated back spatially; direction planes are NOT permuted, as in the
+ * reference) and mean value over the 8 dihedral images of each position, all 8n images in one batch */
+int az_net_forward_sym8(az_context *ctx, const float *features, int n, int mode, float *logits, float *values);
 /* device-resident: d_features float32 [n][196]; d_logits [n][833]; d_values [n]; context stream, no sync */
 int az_net_forward_dev(az_context *ctx, const void *d_features, int n, int mode, void *d_logits, void *d_values);
 /* fused leaf encoding (self_play_client.cpp:174-202) + forward: d_pos is az_position[n] on the device */

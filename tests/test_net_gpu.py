@@ -144,3 +144,25 @@ def test_errors(ctx, nets):
     with az.Context(0) as fresh:
         with pytest.raises(az.AzError):
             net.forward(fresh, _features(2, 1))      # no weights loaded
+
+
+def test_symmetry_ensembled_evaluation(ctx, nets):
+    """nn_evals.evaluate (nn_evals.py:48-62): the GPU expand / reduce kernels against the NumPy composition of the same
+    steps over our own forward pass (exact up to float32 summation order), and against the fp64 restatement."""
+    from ataxxzero_b200 import net
+    from oracle import net_numpy
+    feats = _features(5, 9)
+    for mode, tol in ((net.FP32, FP32_TOL), (net.BF16, BF16_TOL)):
+        got_p, got_v = net.evaluate_symmetric(ctx, feats, mode)
+        assert got_p.shape == (5, 7, 7, 17) and got_v.shape == (5,)
+        for b in range(5):
+            images = np.stack([np.ascontiguousarray(net.apply_symmetry(feats[b], s)) for s in range(8)])
+            p8, v8 = net.forward(ctx, images, mode)
+            back = [net.apply_symmetry(p8[s], net.inverse_symmetry[s]) for s in range(8)]
+            assert np.abs(got_p[b] - np.mean(back, axis=0)).max() < 1e-6
+            assert abs(got_v[b] - np.mean(v8)) < 1e-6
+            w8, wv8 = net_numpy.forward(images, nets.conv, nets.bn, dtype=np.float64)
+            want = np.mean([net.apply_symmetry(w8[s], net.inverse_symmetry[s]) for s in range(8)], axis=0)
+            assert np.abs(got_p[b] - want).max() < tol and abs(got_v[b] - np.mean(wv8)) < tol
+    p0, v0 = net.evaluate_symmetric(ctx, np.zeros((0, 7, 7, 4), dtype=np.float32))
+    assert len(p0) == 0 and len(v0) == 0
