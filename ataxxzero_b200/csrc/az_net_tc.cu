@@ -54,9 +54,10 @@ struct Cfg {
     static constexpr int IN_BYTES = ACT_ROWS * ROW_BYTES;          // input planes: one k-group (4 real + 4 zero channels)
     static constexpr int OFF_ACT = 0;
     static constexpr int OFF_RING = OFF_ACT + ACT_BYTES;
-    static constexpr int OFF_IN = OFF_RING + STAGES * STAGE_BYTES;
-    static constexpr int OFF_ZERO = OFF_IN + IN_BYTES;
-    static constexpr int OFF_SHIFT = OFF_ZERO + ZERO_BYTES;        // float[TILES][2][F]: per-layer BN shifts, double-buffered
+    // The input planes are staged in k-group 0 of the activation buffer itself: it is dead between the heads of one unit
+    // and the layer-0 epilogue of the next (which overwrites it only after the input-conv MMAs have completed).
+    static constexpr int OFF_IN = OFF_ACT;
+    static constexpr int OFF_SHIFT = OFF_RING + STAGES * STAGE_BYTES;   // float[TILES][2][F]: per-layer BN shifts, double-buffered
     static constexpr int OFF_VPART = OFF_SHIFT + TILES * 2 * F * 4;
     static constexpr int OFF_BAR = OFF_VPART + 64;
     static constexpr int NUM_BARS = 2 * STAGES + 2 * TILES + 1;    // full/empty ring, acc_full/act_ready per tile, input staged
@@ -298,8 +299,6 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
 
     // ---- one-time setup ----
     for (int i = threadIdx.x; i < C::ACT_BYTES / 16; i += C::NUM_THREADS) reinterpret_cast<uint4 *>(smem + C::OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < (C::IN_BYTES + ZERO_BYTES) / 16; i += C::NUM_THREADS)
-        reinterpret_cast<uint4 *>(smem + C::OFF_IN)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), CS); }
         for (int t = 0; t < TILES; ++t) { mbar_init(bar(B_ACC + t), 1); mbar_init(bar(B_ACT + t), 128); }
@@ -371,7 +370,8 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                         for (int j = part * 4; j < (part ? 5 : 4); ++j) {
                             const int tap0 = 2 * j, tap1 = 2 * j + 1;
                             const uint32_t a0 = in_rows + ((tap0 / 3 - 1) * 8 + (tap0 % 3 - 1)) * ROW_BYTES;
-                            const uint32_t a1 = tap1 < 9 ? in_rows + ((tap1 / 3 - 1) * 8 + (tap1 % 3 - 1)) * ROW_BYTES : sbase + C::OFF_ZERO;
+                            // the 10th "tap" has all-zero weights: any finite rows will do, take the next row
+                            const uint32_t a1 = tap1 < 9 ? in_rows + ((tap1 / 3 - 1) * 8 + (tap1 % 3 - 1)) * ROW_BYTES : a0 + ROW_BYTES;
                             umma(tmem_base + C::TM_ACC + t * 128, make_desc(a0, a1 - a0), make_desc(b_rows + (j - part * 4) * 2 * W_LBO, W_LBO),
                                  IDESC_128, j > 0);
                         }
