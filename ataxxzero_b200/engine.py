@@ -43,11 +43,17 @@ def initialize_model(path, device=0, seed=None):
 
 
 def setup_evaluator(use_rpc=False, temperature=0.0):
-    """engine.py:29-38.  The gevent/mprpc transport is not part of this package."""
+    """engine.py:29-38.  ``use_rpc``: evaluate through a running ``ataxxzero_b200.gpu_server`` (port 6000) instead of a
+    local context; that evaluator serves NNEvaluator-style ``populate`` calls, the device-resident MCTS always uses the
+    local network."""
     global global_evaluator
     if use_rpc:
-        raise NotImplementedError("RPC evaluation (gpu_server.py / rpc_client.py) is out of scope; evaluate locally")
-    global_evaluator = NNEvaluator(temperature=temperature)
+        print("Using RPC evaluator.")
+        from . import rpc_client
+        rpc_client.setup_rpc()
+        global_evaluator = rpc_client.RPCEvaluator(temperature=temperature)
+    else:
+        global_evaluator = NNEvaluator(temperature=temperature)
 
 
 def sample_by_weight(weights):

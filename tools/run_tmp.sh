@@ -1,2 +1,3 @@
-python -m pytest tests/test_mcts_gpu.py tests/test_selfplay_gpu.py -x -q 2>&1 | tail -3
-for lv in 48 64 80; do AZ_POOL_PROFILE=1 AZ_LEVELS_PER_TICK=$lv timeout 200 python tools/tick_timing.py 2048 800 1024 2>&1 | grep -v "^$" | grep -v "populate\|backup\|expand\|make_move"; done
+python tools/profile_pool.py 2048 800 64 > gpurun_out/pool_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"k_tree_tick" -s 60 -c 2 -o gpurun_out/tree_r01b python tools/profile_pool.py 2048 800 64 > gpurun_out/ncu_tree_b.log 2>&1
+tail -2 gpurun_out/ncu_tree_b.log
