@@ -110,3 +110,53 @@ def test_legacy_link_contract(tmp_path, ctx, oracle):
     i = link.get_workload()
     assert i in (0, 1)
     link.shutdown()
+
+
+def test_full_size_pool_properties(tmp_path, ctx, oracle):
+    """BASELINE configs[3] per-GPU shard (2048 games x 800 visits, bf16 net, noise on) started from late-game positions so
+    that games finish within the test: size-independent properties instead of a CPU re-run -- every finished record
+    replays legally from its first board, every distribution is k/N with N >= 800 and sums to 1, counters add up."""
+    import random
+    from ataxxzero_b200 import model, net, rules, search
+    from oracle.cpu import START_FEN
+    net.load_weights(ctx, model.Network.random_init(seed=0))
+    rng = random.Random(4)
+    roots, start = [], oracle.set_board(START_FEN)
+    while len(roots) < 2048:
+        p = start
+        for _ in range(rng.randrange(90, 170)):
+            mv = oracle.movegen(p)
+            if not mv or oracle.result(p):
+                break
+            p = oracle.makemove(p, rng.choice(mv))
+        if oracle.result(p) == 0 and oracle.movegen(p):
+            roots.append(p)
+    arr = np.zeros(2048, dtype=rules.POSITION_DTYPE)
+    for i, p in enumerate(roots):
+        arr[i] = (p.ply, p.turn, p.blockers, (p.pieces[0], p.pieces[1]))
+    out = str(tmp_path / "full.json")
+    with search.Pool(ctx, 2048, 800, eval_mode=search.EVAL_BF16, noise=True, auto_play=True, seed=21) as pool:
+        pool.set_roots(arr)
+        stats = pool.selfplay(out, target_games=150, max_seconds=120)
+    assert stats["games_finished"] >= 150 and stats["evals"] > 0
+    assert stats["steps"] >= stats["terminal_steps"] and stats["max_depth"] < 1024
+    lines = open(out).read().splitlines()
+    assert len(lines) >= 150
+    first_boards = {tuple(oracle.board_json(p)): p for p in roots}
+    checked = 0
+    for ln in lines:
+        game = json.loads(ln)
+        p = first_boards.get(tuple(game["boards"][0]))
+        if p is None:                      # a game restarted from the standard opening after its slot's first game ended
+            p = start
+        for board, move, dist in zip(game["boards"], game["moves"], game["dists"]):
+            assert board == oracle.board_json(p) and oracle.result(p) == 0
+            legal = {oracle.move_string(m): m for m in oracle.movegen(p)}
+            assert move in dist and set(dist) <= set(legal)
+            assert abs(sum(dist.values()) - 1.0) < 1e-9
+            smallest = min(dist.values())
+            assert 0 < smallest and 1.0 / smallest < 5000          # k/N with 800 <= N (carried visits keep N near 800)
+            p = oracle.makemove(p, legal[move])
+            checked += 1
+        assert oracle.result(p) == game["result"]
+    assert checked >= 150
