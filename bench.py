@@ -402,6 +402,10 @@ def run_ours(args):
         nodes = rules.perft(ctx, p, depth)
         dt = time.perf_counter() - t0
         perft["depth%d" % depth] = {"nodes": nodes, "mnodes_per_s": nodes / dt / 1e6}
+    try:        # integer-ALU roofline of the perft walk kernel, from the committed ncu capture (profiles/)
+        perft["k_walk_alu_pipe_pct_of_peak_ncu"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_walk"]["alu_pipe_pct_of_peak_active"]
+    except Exception:
+        pass
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": k, "warmup": w,
             "ms_per_step": ms / k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
