@@ -119,6 +119,17 @@ def add_dirichlet_noise_to_posterior(posterior, alpha, weight):
     return {move: (1.0 - weight) * prob + weight * n for (move, prob), n in zip(posterior.items(), noise)}
 
 
+def posterior_from_logits(board, raw, temperature=0.0):
+    """Raw policy logits [7,7,17] -> prior over the board's legal moves (engine.py:194-203 / rpc_client.py:22-29):
+    optional Gaussian logit noise, softmax, gather per move, renormalise with the reference's +1e-6."""
+    if temperature:
+        raw = raw + np.random.randn(*raw.shape) * temperature
+    sm = softmax(raw)
+    posterior = {move: float(get_move_score(sm, move)) for move in board.legal_moves()}
+    denominator = sum(posterior.values()) + 1e-6
+    return {move: p / denominator for move, p in posterior.items()}
+
+
 class NNEvaluator:
     """engine.py:121-233: evaluation cache in front of the network.  ``evaluate`` runs the GPU net."""
     MAXIMUM_CACHE_ENTRIES = 200000
@@ -158,12 +169,7 @@ class NNEvaluator:
         features = np.stack([board_to_features(b) for b in ensemble])
         posteriors, values = net.forward(context, features, eval_mode)
         for board, raw, (value,) in zip(ensemble, posteriors, values):
-            if self.temperature:
-                raw = raw + np.random.randn(*raw.shape) * self.temperature
-            sm = softmax(raw)
-            posterior = {move: float(get_move_score(sm, move)) for move in board.legal_moves()}
-            denominator = sum(posterior.values()) + 1e-6
-            posterior = {move: p / denominator for move, p in posterior.items()}
+            posterior = posterior_from_logits(board, raw, self.temperature)
             self.cache[NNEvaluator.board_key(board)] = NNEvaluator.Entry(board, float(value), posterior, False)
 
     def populate(self, board):
