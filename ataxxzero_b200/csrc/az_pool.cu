@@ -314,7 +314,9 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
             if (env) D.cap = atoi(env) > 0 ? std::min(atoi(env), D.G) : D.G;
             else if (D.G >= round) D.cap = D.G / round * round;
         }
-        D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : 48;
+        // the level budget trims the tail of a tick over thousands of games; a handful of trees has no tail to trim, and a
+        // suspended descent would cost it a whole (empty) net launch
+        D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : (cfg->games < 64 ? (1 << 20) : 48);
         D.seed = cfg->seed;
         D.rec_cap_words = rec_cap_words;
         const size_t G = (size_t)D.G;
@@ -476,15 +478,24 @@ extern "C" int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out)
     AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_run: null pool");
     AZ_REQUIRE(pool->cfg.eval_mode != AZ_EVAL_EXTERNAL, AZ_ERR_STATE, "az_pool_run: pool uses an external evaluator (collect/provide)");
     if (idle_out) *idle_out = 0;
-    for (int t = 0; t < max_ticks; ++t) {
-        bool idle = true;
-        for (Group &grp : pool->groups) {
-            int rc = launch_tree(pool, grp);
-            if (rc) return rc;
-            AZ_CUDA(cudaMemcpyAsync(grp.h_counts, grp.dev.req_count + 2 * grp.slot, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, grp.stream));
-            if ((rc = launch_net(pool, grp))) return rc;
+    // Ticks are launched in bursts and the "anything left to do?" counters are read back once per burst: a tick of an
+    // idle pool is two empty kernels, far cheaper than a host round trip per tick (single-tree searches are
+    // latency-bound: one leaf per tick).  The burst doubles up to 16 while the pool stays busy.
+    int burst = 1;
+    for (int t = 0; t < max_ticks;) {
+        const int n = std::min(burst, max_ticks - t);
+        for (int k = 0; k < n; ++k) {
+            for (Group &grp : pool->groups) {
+                int rc = launch_tree(pool, grp);
+                if (rc) return rc;
+                if (k == n - 1)
+                    AZ_CUDA(cudaMemcpyAsync(grp.h_counts, grp.dev.req_count + 2 * grp.slot, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, grp.stream));
+                if ((rc = launch_net(pool, grp))) return rc;
+            }
+            pool->ticks++;
         }
-        pool->ticks++;
+        t += n;
+        bool idle = true;
         for (Group &grp : pool->groups) {
             AZ_CUDA(cudaStreamSynchronize(grp.stream));
             idle &= grp.h_counts[0] == 0 && grp.h_counts[1] == 0;   // no requests, nobody mid-step: every tree is done (or stalled)
@@ -493,6 +504,7 @@ extern "C" int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out)
             if (idle_out) *idle_out = 1;
             break;
         }
+        burst = std::min(2 * burst, 16);
     }
     AZ_CUDA(cudaGetLastError());
     return check_game_errors(pool);
