@@ -56,7 +56,7 @@ struct az_pool {
     az_context *ctx = nullptr;
     az_pool_config cfg{};
     std::vector<Group> groups;
-    int per_group = 0;                    // games per group (the last group may hold fewer)
+    std::vector<int> group_size;          // games per group (sums to cfg.games)
     int net_tiles = 0;                    // net kernel variant used by this pool (0 = context default)
     int pending_requests = 0;             // external mode: requests handed out by collect()
     uint64_t ticks = 0, launches = 0;
@@ -65,8 +65,9 @@ struct az_pool {
 
     Group &group_of(int game, int *local)
     {
-        const int gi = game / per_group;
-        *local = game - gi * per_group;
+        size_t gi = 0;
+        while (gi + 1 < groups.size() && game >= groups[gi + 1].first_game) ++gi;
+        *local = game - groups[gi].first_game;
         return groups[gi];
     }
     int G() const { return cfg.games; }
@@ -278,7 +279,26 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         const char *tiles_env = getenv("AZ_POOL_NET_TILES");
         if (tiles_env) pool->net_tiles = atoi(tiles_env) == 1 ? 1 : atoi(tiles_env) == 2 ? 2 : 0;
     }
-    pool->per_group = (cfg->games + n_groups - 1) / n_groups;
+    // group sizes: equal shares, or AZ_POOL_SPLIT="1536,512" (an asymmetric split lets the small group's net launch
+    // hide inside the big group's tree kernel and vice versa)
+    pool->group_size.assign(n_groups, 0);
+    for (int gi = 0; gi < n_groups; ++gi) pool->group_size[gi] = cfg->games / n_groups + (gi < cfg->games % n_groups ? 1 : 0);
+    if (const char *split = pipelined ? getenv("AZ_POOL_SPLIT") : nullptr) {
+        std::vector<int> sizes;
+        int total = 0;
+        for (const char *p = split; *p;) {
+            char *end = nullptr;
+            const long v = strtol(p, &end, 10);
+            if (end == p || v <= 0) { sizes.clear(); break; }
+            sizes.push_back((int)v);
+            total += (int)v;
+            p = *end == ',' ? end + 1 : end;
+        }
+        if (!sizes.empty() && total == cfg->games && sizes.size() <= 4) {
+            pool->group_size = sizes;
+            n_groups = (int)sizes.size();
+        }
+    }
     pool->groups.resize(n_groups);
 
     size_t free_b = 0, total_b = 0;
@@ -295,9 +315,9 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
     int rc = 0;
     for (int gi = 0; gi < n_groups && rc == 0; ++gi) {
         Group &grp = pool->groups[gi];
-        grp.first_game = gi * pool->per_group;
+        grp.first_game = gi == 0 ? 0 : pool->groups[gi - 1].first_game + pool->group_size[gi - 1];
         PoolDev &D = grp.dev;
-        D.G = std::min(pool->per_group, cfg->games - grp.first_game);
+        D.G = pool->group_size[gi];
         D.C = pool->cfg.node_capacity;
         D.visits = cfg->visits;
         D.max_plies = pool->cfg.max_plies;
@@ -310,7 +330,12 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         D.cap = D.G;
         if (pipelined) {
             const int round = az_net_tc_boards_per_round(ctx, pool->net_tiles);
-            const char *env = getenv("AZ_REQ_CAP");
+            const char *env = getenv("AZ_REQ_CAP");            // one value, or one per group ("1184,444")
+            for (int k = 0; env && k < gi; ++k) {
+                const char *comma = strchr(env, ',');
+                if (!comma) break;
+                env = comma + 1;
+            }
             if (env) D.cap = atoi(env) > 0 ? std::min(atoi(env), D.G) : D.G;
             else if (D.G >= round) D.cap = D.G / round * round;
         }
