@@ -55,6 +55,62 @@ def random_play_games(ctx, count, rng=random, start_fen="x5o/7/7/7/7/7/o5x x"):
     return entries
 
 
+class UAIPlayer:
+    """A UAI engine in a subprocess (what ``--supervised CMD`` talks to; the reference keeps this class in
+    uai_ringmaster.py:9-60): ``set_state(board)`` sends the FEN, ``genmove(ms)`` asks for a move."""
+
+    def __init__(self, cmd):
+        import shlex
+        import subprocess
+        self.cmd = shlex.split(cmd) if isinstance(cmd, str) else list(cmd)
+        self.proc = subprocess.Popen(self.cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        for line in ("uai", "isready", "uainewgame"):
+            self.send(line)
+
+    def send(self, text):
+        self.proc.stdin.write((text + "\n").encode("utf8"))
+        self.proc.stdin.flush()
+
+    def set_state(self, board):
+        self.send("position fen %s" % board.fen())
+
+    def genmove(self, ms=1000):
+        from .uai_interface import uai_decode_move
+        self.send("go movetime %i" % ms)
+        while True:
+            line = self.proc.stdout.readline().decode("utf8")
+            if not line:
+                raise ValueError("the UAI engine %r closed its output" % (self.cmd,))
+            if line.startswith("bestmove "):
+                return uai_decode_move(line.split()[1])
+
+    def quit(self):
+        try:
+            self.send("quit")
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+
+
+def supervised_game(args):
+    """Record a game played by an external UAI engine (generate_games.py:27-36): its move is both played and the target."""
+    board = ataxx_rules.AtaxxState.initial()
+    entry = {"boards": [], "moves": []}
+    for ply in range(MAXIMUM_GAME_PLIES):
+        args.uai_player.set_state(board)
+        move = args.uai_player.genmove(args.supervised_ms)
+        if move not in board.legal_moves():
+            raise ValueError("illegal move %r from the UAI engine at %s" % (move, board.fen()))
+        entry["boards"].append(list(board.board))
+        entry["moves"].append(_json_move(move) if move != "pass" else "pass")
+        board.move(move)
+        if board.result() is not None:
+            break
+    entry["result"] = board.result()
+    print("[%3i] Generated a %i ply game with result %r." % (args.group_index, len(entry["boards"]), entry["result"]))
+    return entry
+
+
 def mcts_game(args, engine):
     """One self-play game driven through the engine.py interface (generate_games.py:16-77)."""
     board = ataxx_rules.AtaxxState.initial()
@@ -107,6 +163,9 @@ def build_parser():
     parser.add_argument("--show-game", action="store_true", help="Show the game while it's generating.")
     parser.add_argument("--game-count", metavar="N", default=None, type=int, help="Maximum number of games to generate.")
     parser.add_argument("--no-write", action="store_true", help="Don't write out generated games at all.")
+    parser.add_argument("--supervised", metavar="CMD", default=None, type=str, help="Command for a UAI engine.")
+    parser.add_argument("--supervised-ms", metavar="N", default=100, type=int,
+                        help="Number of milliseconds per move for supervised generation.")
     parser.add_argument("--device", metavar="N", default=0, type=int, help="GPU index.")
     parser.add_argument("--seed", metavar="N", default=None, type=int, help="Seed for Python's RNG (random play).")
     return parser
@@ -146,6 +205,13 @@ def main(argv=None):
                 while written < target:
                     for entry in random_play_games(ctx, min(4096, target - written)):
                         emit(entry)
+        elif args.supervised is not None:
+            args.uai_player = UAIPlayer(args.supervised)
+            try:
+                while args.game_count is None or written < args.game_count:
+                    emit(supervised_game(args))
+            finally:
+                args.uai_player.quit()
         else:
             from .. import engine
             engine.setup_evaluator(use_rpc=False, temperature=LOGIT_TEMPERATURE)

@@ -424,6 +424,14 @@ def run_ours(args):
         pool.close()
         try:
             line["cpu_baseline"] = reference_sample(args.cpu_seconds, visits)
+            # second metric of BASELINE.json: the reference's own movegen/makemove (oracle/_ref/perft_ref) on the host cores
+            from oracle import cpu as ocpu
+            if os.path.exists(ocpu.REF_PERFT):
+                cores = os.cpu_count() or 1
+                n1, s1 = ocpu.ref_perft(ocpu.OPEN_FEN, 6, 1)
+                nN, sN = ocpu.ref_perft(ocpu.OPEN_FEN, 7, cores)
+                line["cpu_baseline"]["perft"] = {"kind": "reference", "depth6_1thread_mnodes_per_s": n1 / s1 / 1e6,
+                                                 "depth7_%dthreads_mnodes_per_s" % cores: nN / sN / 1e6, "nodes": [n1, nN]}
         except Exception as exc:        # the baseline is reported, never the product path
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable",
                                     "sample": "failed: %r" % (exc,)}

@@ -130,3 +130,41 @@ def test_looper_paths_and_counts(tmp_path):
     (tmp_path / "games").mkdir()
     open(paths[0], "w").write("{}\n\n{}\n")
     assert looper.count_games(paths) == 2
+
+
+def test_generate_games_supervised_with_a_scripted_uai_engine(tmp_path):
+    """--supervised CMD (generate_games.py:27-36,98-99): games recorded from an external UAI engine; here a scripted
+    engine that answers `go movetime` with a random legal move.  No GPU involved."""
+    import json
+    import sys
+    from conftest import ROOT
+    from ataxxzero_b200 import ataxx_rules as ar
+    from ataxxzero_b200.cli import generate_games
+    script = tmp_path / "fake_uai.py"
+    script.write_text(
+        "import sys, random\n"
+        "sys.path.insert(0, %r)\n"
+        "from ataxxzero_b200 import ataxx_rules\n"
+        "from ataxxzero_b200.cli.uai_interface import uai_encode_move\n"
+        "board, rng = ataxx_rules.AtaxxState.initial(), random.Random(1)\n"
+        "for line in sys.stdin:\n"
+        "    line = line.strip()\n"
+        "    if line == 'quit': break\n"
+        "    if line == 'uai': print('uaiok')\n"
+        "    elif line == 'isready': print('readyok')\n"
+        "    elif line.startswith('position fen '): board = ataxx_rules.AtaxxState.from_fen(line[13:])\n"
+        "    elif line.startswith('go '): print('bestmove ' + uai_encode_move(rng.choice(board.legal_moves())))\n"
+        "    sys.stdout.flush()\n" % ROOT)
+    out = tmp_path / "sup.json"
+    n = generate_games.main(["--supervised", "%s %s" % (sys.executable, script), "--supervised-ms", "1", "--game-count", "2",
+                             "--output-games", str(out)])
+    assert n == 2
+    for line in out.read_text().splitlines():
+        game = json.loads(line)
+        board = ar.AtaxxState.initial()
+        for cells, move in zip(game["boards"], game["moves"]):
+            assert list(board.board) == cells
+            mv = ("c", tuple(move[1])) if move[0] == "c" else (tuple(move[0]), tuple(move[1]))
+            assert mv in board.legal_moves()
+            board.move(mv)
+        assert board.result() == game["result"]
