@@ -39,6 +39,12 @@ def load_weights(ctx, network):
     return network
 
 
+def load_packed(ctx, packed, filters=128, blocks=12):
+    """Upload an already packed float32 parameter vector (``Network.packed()``), e.g. one kept in pinned host memory."""
+    packed = np.ascontiguousarray(packed, dtype=np.float32)
+    check(lib().az_net_load(ctx.handle, _ptr(packed), packed.size, int(filters), int(blocks)))
+
+
 def forward(ctx, features, mode=BF16):
     """features: float32/int8 array [B,7,7,4] (or [B,196]) -> (logits [B,7,7,17], values [B,1])."""
     feats = np.asarray(features)

@@ -347,8 +347,10 @@ def run_ours(args):
     ctx.sync()
     e0 = pool.stats()
     t0 = time.perf_counter()
+    pinned = torch.from_numpy(packed).pin_memory()       # the step's input lives in pinned host memory
+    pinned_np = pinned.numpy()
     for _ in range(k):
-        net.load_weights(ctx, network)                   # H2D: the step's input (host-resident .npy weights)
+        net.load_packed(ctx, pinned_np, network.filters, network.blocks)   # H2D: the weights of the .npy, every step
         pool.selfplay_ticks(ticks, out_path)             # D2H: finished games -> JSON lines on the host
     ctx.sync()
     e2e_s = allreduce(time.perf_counter() - t0, "max")
@@ -363,7 +365,7 @@ def run_ours(args):
         json_bytes = 0
     e2e = {"value": e2e_positions / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(packed.nbytes),
            "d2h_bytes_per_step": int(record_bytes / k), "json_bytes_per_step": int(json_bytes / k),
-           "api": "net.load_weights + Pool.selfplay_ticks(ticks, path) -> az_net_load / az_selfplay_ticks"}
+           "api": "net.load_packed (pinned host weights) + Pool.selfplay_ticks(ticks, path) -> az_net_load / az_selfplay_ticks"}
 
     # ---- BASELINE configs[4]: single-tree search (replicas only, rank 0) + leaf-batch latency of the net kernel ----
     single = {}
