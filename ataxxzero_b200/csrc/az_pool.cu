@@ -641,7 +641,7 @@ extern "C" int az_pool_pv(az_pool *pool, int game, az_move *moves, int32_t *visi
         moves[n] = reinterpret_cast<const uint16_t *>(slot.data() + kOffMove)[best];
         if (visits) visits[n] = (int32_t)nv[best];
         ++n;
-        node = ch[best];
+        node = ch[best] & kChildMask;
     }
     *len_out = n;
     return AZ_OK;

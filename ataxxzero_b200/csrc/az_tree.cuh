@@ -28,6 +28,10 @@ namespace aztree {
 constexpr int kNodeStride = 9216;
 constexpr int kOffP = 64, kOffW = 2112, kOffQ = 4160, kOffN = 6208, kOffChild = 7232, kOffMove = 8256, kOffRank = 8768;
 constexpr int kMaxPath = 1024;
+// child[] entries: bits 0..23 node index, bits 24..27 ceil(L_child / 32) -- how many 32-child groups a descent must
+// load for that child, so a level fetches the child's real fan-out instead of a fixed 128 entries; -1 = no edge yet
+constexpr int32_t kChildMask = 0x00ffffff;
+constexpr int kChildGroupShift = 24;
 constexpr int kRecWordsPerPly = 6 + 2 * 256;    // worst-case record words per ply
 
 enum : uint32_t {
