@@ -647,6 +647,35 @@ extern "C" int az_pool_pv(az_pool *pool, int game, az_move *moves, int32_t *visi
     return AZ_OK;
 }
 
+// Debug / analysis hook (not in the public header): positions (own, opp, turn) of every node reachable from the root
+// of `game`, breadth first.  Used to measure how many leaves of a search are transpositions of each other.
+extern "C" int az_pool_debug_nodes(az_pool *pool, int game, uint64_t *own, uint64_t *opp, int32_t *turn, int32_t *visits, int max_nodes,
+                                   int32_t *n_out)
+{
+    AZ_REQUIRE(pool && own && opp && turn && n_out, AZ_ERR_ARG, "az_pool_debug_nodes: bad argument");
+    int local;
+    Group &grp = pool->group_of(game, &local);
+    AZ_CUDA(cudaStreamSynchronize(grp.stream));
+    Game gm;
+    AZ_CUDA(cudaMemcpy(&gm, grp.dev.games + local, sizeof(Game), cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> arena((size_t)grp.dev.C * kNodeStride);
+    AZ_CUDA(cudaMemcpy(arena.data(), grp.dev.nodes + (size_t)local * grp.dev.C * kNodeStride, arena.size(), cudaMemcpyDeviceToHost));
+    std::vector<int> queue{gm.root};
+    int n = 0;
+    for (size_t q = 0; q < queue.size() && n < max_nodes; ++q) {
+        const uint8_t *nd = arena.data() + (size_t)queue[q] * kNodeStride;
+        const NodeHdr *h = reinterpret_cast<const NodeHdr *>(nd);
+        own[n] = h->own; opp[n] = h->opp; turn[n] = h->turn;
+        if (visits) visits[n] = h->N;
+        ++n;
+        const int32_t *ch = reinterpret_cast<const int32_t *>(nd + kOffChild);
+        for (int i = 0; i < h->n_moves; ++i)
+            if (ch[i] >= 0) queue.push_back(ch[i] & kChildMask);
+    }
+    *n_out = n;
+    return AZ_OK;
+}
+
 extern "C" int az_pool_play(az_pool *pool, int game, az_move move)
 {
     AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_play: null pool");
