@@ -63,6 +63,7 @@ _SIGNATURES = {
     "az_perft": (C.c_int, [_vp, C.POINTER(Position), C.c_int, C.POINTER(C.c_uint64)]),
     "az_perft_batch_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
     "az_perft_last_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "az_random_playouts": (C.c_int, [_vp, C.POINTER(Position), C.c_int, C.c_int, C.c_uint64, _vp, _vp, _vp]),
 }
 
 

@@ -25,33 +25,29 @@ def _json_move(move):
     return list(map(list, move)) if move[0] != "c" else ["c", list(move[1])]
 
 
-def random_play_games(ctx, count, rng=random, start_fen="x5o/7/7/7/7/7/o5x x"):
-    """`count` uniformly random games played concurrently; yields finished entries (result None is possible at 400 plies)."""
-    import numpy as np
-    start = ataxx_rules.AtaxxState.from_fen(start_fen)
-    arr = rules.positions_array([start.to_position()] * count)
-    entries = [{"boards": [], "moves": []} for _ in range(count)]
-    live = np.arange(count)
-    results = [None] * count
-    for ply in range(MAXIMUM_GAME_PLIES):
-        if len(live) == 0:
-            break
-        lists = rules.movegen_batch(ctx, arr[live])
-        picked = []
-        for g, mv in zip(live, lists):
-            st = ataxx_rules.AtaxxState.from_position(rules.array_to_positions(arr[g:g + 1])[0])
-            m = rng.choice(mv)
-            entries[g]["boards"].append(list(st.board))
-            entries[g]["moves"].append(_json_move(rules.to_reference_move(m)))
-            picked.append(m)
-        arr[live] = rules.makemove_batch(ctx, arr[live], picked)
-        res = rules.result_batch(ctx, arr[live])
-        for g, r in zip(live, res):
-            if r:
-                results[g] = int(r)
-        live = live[res == 0]
+_BOARD_LUT = None
+
+
+def _board_cells(x, o):
+    """49 ints (1 = x, 2 = o), index x + 7*y with y = 0 at the top, from the two piece bitboards (bit sq = x + 7*(6-y))."""
+    global _BOARD_LUT
+    if _BOARD_LUT is None:
+        _BOARD_LUT = [(i % 7) + 7 * (6 - i // 7) for i in range(49)]
+    return [1 if x >> sq & 1 else 2 if o >> sq & 1 else 0 for sq in _BOARD_LUT]
+
+
+def random_play_games(ctx, count, seed=0, start_fen="x5o/7/7/7/7/7/o5x x"):
+    """`count` uniformly random games played on the GPU (az_random_playouts: one thread per game); returns the entries in
+    the reference's Python record format.  `result` is None for a game that reached 400 plies undecided."""
+    start = ataxx_rules.AtaxxState.from_fen(start_fen).to_position()
+    plies, n_plies, results = rules.random_playouts(ctx, start, count, MAXIMUM_GAME_PLIES, seed)
+    entries = []
     for g in range(count):
-        entries[g]["result"] = results[g]
+        n = int(n_plies[g])
+        xs, os_, mvs = plies["x"][g, :n].tolist(), plies["o"][g, :n].tolist(), plies["move"][g, :n].tolist()
+        entries.append({"boards": [_board_cells(x, o) for x, o in zip(xs, os_)],
+                        "moves": [_json_move(rules.to_reference_move((m & 0xff, m >> 8))) for m in mvs],
+                        "result": int(results[g]) or None})
     return entries
 
 
@@ -202,9 +198,12 @@ def main(argv=None):
             print("Doing random play! Loading no model, and not using RPC.")
             with Context(device=args.device) as ctx:
                 target = args.game_count if args.game_count is not None else 1 << 62
+                batch = 0
                 while written < target:
-                    for entry in random_play_games(ctx, min(4096, target - written)):
+                    seed = (args.seed if args.seed is not None else random.getrandbits(62)) + batch
+                    for entry in random_play_games(ctx, min(4096, target - written), seed=seed):
                         emit(entry)
+                    batch += 1
         elif args.supervised is not None:
             args.uai_player = UAIPlayer(args.supervised)
             try:

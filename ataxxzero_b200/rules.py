@@ -172,3 +172,17 @@ def perft_last_stats(ctx):
     fr = C.c_int32()
     check(lib().az_perft_last_stats(ctx.handle, C.byref(cn), C.byref(la), C.byref(fr)))
     return {"count_nodes": cn.value, "launches": la.value, "frontier_items": fr.value}
+
+
+PLAYOUT_DTYPE = np.dtype([("x", "<u8"), ("o", "<u8"), ("move", "<u4"), ("pad", "<u4")])
+
+
+def random_playouts(ctx, start, n_games, max_plies=400, seed=0):
+    """``n_games`` uniformly random games from ``start`` played on the GPU (generate_games.py --random-play).
+    Returns (plies [n_games, max_plies] structured array of PLAYOUT_DTYPE, n_plies [n_games], result [n_games])."""
+    plies = np.zeros((max(n_games, 1), max_plies), dtype=PLAYOUT_DTYPE)
+    n_plies = np.zeros(max(n_games, 1), dtype=np.int32)
+    result = np.zeros(max(n_games, 1), dtype=np.int32)
+    check(lib().az_random_playouts(ctx.handle, C.byref(start), int(n_games), int(max_plies), int(seed) & (2**64 - 1), _ptr(plies),
+                                   _ptr(n_plies), _ptr(result)))
+    return plies[:n_games], n_plies[:n_games], result[:n_games]

@@ -395,6 +395,13 @@ def run_ours(args):
             lat["batch%d" % b] = {"p50_us": samples[len(samples) // 2], "p99_us": samples[-1]}
         single["leaf_batch_latency_host_to_host"] = lat
 
+    # ---- BASELINE configs[0]: uniformly random play, 2000 games, on the device (records copied back to the host) ----
+    start = rules.set_board(rules.OPEN_FEN)
+    rules.random_playouts(ctx, start, 2000, 400, seed=1)
+    t0 = time.perf_counter()
+    _, n_plies, _ = rules.random_playouts(ctx, start, 2000, 400, seed=2)
+    random_play = {"games": 2000, "positions": int(n_plies.sum()), "positions_per_s": float(n_plies.sum()) / (time.perf_counter() - t0)}
+
     # ---- secondary metric of BASELINE.json: perft Mnodes/s (device time incl. frontier expansion) ----
     perft = {}
     for depth in (7, 8):
@@ -421,7 +428,7 @@ def run_ours(args):
             "e2e": e2e, "roofline": roofline, "clocks": clocks, "gpu_launches": int(d["kernel_launches"]),
             "extra": {"leaf_evals_per_s": evals / (ms * 1e-3), "mcts_steps_per_s": steps / (ms * 1e-3),
                       "evals_per_position": evals / max(positions, 1), "max_depth": s1["max_depth"], "perft": perft,
-                      "single_tree": single}}
+                      "single_tree": single, "random_play": random_play}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pool.close()
         try:

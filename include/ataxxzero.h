@@ -92,6 +92,14 @@ int az_perft_batch_dev(az_context *ctx, const void *d_pos, int n, int depth, voi
 /* statistics of the last perft call: device-side counted parents ("count nodes") and kernel launches */
 int az_perft_last_stats(az_context *ctx, uint64_t *count_nodes, int32_t *launches, int32_t *frontier_items);
 
+/* ---------------- random play (generate_games.py --random-play, generate_games.py:20-24,50-57) ------------- */
+/* n_games uniformly random games from `start`, played on the device (one move drawn uniformly from the legal moves per
+ * ply, Philox stream keyed by seed and game).  plies_out: n_games x max_plies records of 24 bytes {uint64 x, uint64 o
+ * (pieces BEFORE the move), uint32 move = from | to << 8, uint32 0}; n_plies_out[g] plies were played; result_out[g] is
+ * 1 / 2, or 0 when max_plies was reached first (the reference skips such games).  All outputs are host memory. */
+int az_random_playouts(az_context *ctx, const az_position *start, int n_games, int max_plies, uint64_t seed, void *plies_out,
+                       int32_t *n_plies_out, int32_t *result_out);
+
 /* ---------------- network (model.py:38-79 forward; .npy weights model.py:179-196) ------------- */
 /* Precision modes of the forward pass. */
 #define AZ_NET_FP32   0   /* CUDA-core fp32, reference-accurate (<= 1e-5 vs the fp32/fp64 restatement) */

@@ -104,3 +104,34 @@ def test_empty_batches(ctx):
     assert rules.movegen_batch(ctx, []) == []
     assert len(rules.result_batch(ctx, [])) == 0
     assert len(rules.perft_batch(ctx, [], 3)) == 0
+
+
+def test_random_playouts_on_device(ctx, oracle):
+    """az_random_playouts: every game replays legally through the oracle (boards, moves, adjudication), the games differ,
+    the same seed reproduces them, and the length statistics look like the reference's random play (SURVEY App. C-4:
+    mean ~185 plies)."""
+    import numpy as np
+    from ataxxzero_b200 import rules
+    from oracle.cpu import OPEN_FEN, START_FEN
+    for fen in (OPEN_FEN, START_FEN):
+        start = rules.set_board(fen)
+        plies, n_plies, result = rules.random_playouts(ctx, start, 600, 400, seed=5)
+        again = rules.random_playouts(ctx, start, 600, 400, seed=5)
+        assert np.array_equal(plies["move"], again[0]["move"]) and np.array_equal(n_plies, again[1])
+        other = rules.random_playouts(ctx, start, 600, 400, seed=6)
+        assert not np.array_equal(n_plies, other[1])
+        for g in range(0, 600, 3):
+            p = oracle.set_board(fen)
+            for k in range(int(n_plies[g])):
+                assert oracle.result(p) == 0
+                assert (int(plies["x"][g, k]), int(plies["o"][g, k])) == (p.pieces[0], p.pieces[1])
+                m = int(plies["move"][g, k])
+                mv = (m & 0xff, m >> 8)
+                assert mv in oracle.movegen(p)
+                p = oracle.makemove(p, mv)
+            assert oracle.result(p) == int(result[g])
+            assert result[g] != 0 or n_plies[g] == 400
+        assert 140 < n_plies[result != 0].mean() < 240
+        first = np.bincount(plies["move"][:, 0], minlength=1)            # 16 legal first moves, each drawn ~1/16 of the time
+        assert (first > 0).sum() == 16 and first[first > 0].min() > 600 / 16 * 0.4
+    assert len(rules.random_playouts(ctx, rules.set_board(OPEN_FEN), 0)[1]) == 0
