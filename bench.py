@@ -146,15 +146,17 @@ class ReferencePipeline:
                 self.evals_per_position = tree.evals / 12.0
         return self.evals_per_position
 
-    def run(self, seconds):
-        """Returns evaluations completed in ~`seconds` of wall time."""
+    def run(self, seconds, evaluator=None):
+        """Returns evaluations completed in ~`seconds` of wall time.  `evaluator(features) -> (policy, value)` replaces
+        the torch-CPU net (used for the host-ceiling / GPU-evaluator variants of the baseline)."""
         np, ctypes = self.np, self.ctypes
         t0 = time.perf_counter()
         evals = 0
+        forward = evaluator or self.net.forward
         if self.kind == "reference":
             while time.perf_counter() - t0 < seconds:
                 i = self.dll.get_workload()
-                policy, value = self.net.forward(self.buffers[i])
+                policy, value = forward(self.buffers[i])
                 policy = np.ascontiguousarray(policy, dtype=np.float32)
                 value = np.ascontiguousarray(value, dtype=np.float32)
                 self.keep = (self.keep + [(policy, value)])[-6:]
@@ -181,16 +183,26 @@ class ReferencePipeline:
                 pass
 
 
-def reference_sample(seconds, visits=VISITS):
+def reference_sample(seconds, visits=VISITS, gpu_evaluator=None):
     pipe = ReferencePipeline(visits)
+    variants = {}
     try:
         epp = pipe.measure_evals_per_position()
         pipe.run(min(2.0, seconds / 4))                     # warm the thread pool / BLAS
         evals, dt = pipe.run(seconds)
+        if pipe.kind == "reference":
+            # BASELINE.md's two other views of the reference: its host side with a free evaluator (the ceiling of the
+            # thread pool + hash-map trees), and the reference client fed by OUR GPU net through its own legacy ABI
+            zeros = (pipe.np.zeros((pipe.B, 7, 7, 17), dtype=pipe.np.float32), pipe.np.zeros((pipe.B, 1), dtype=pipe.np.float32))
+            e0, t0 = pipe.run(4.0, evaluator=lambda f: zeros)
+            variants["zero_cost_evaluator_host_ceiling"] = {"leaf_evals_per_s": e0 / t0, "positions_per_s": e0 / t0 / epp}
+            if gpu_evaluator is not None:
+                e1, t1 = pipe.run(4.0, evaluator=gpu_evaluator)
+                variants["reference_client_with_our_gpu_net"] = {"leaf_evals_per_s": e1 / t1, "positions_per_s": e1 / t1 / epp}
     finally:
         pipe.close()
     cores = os.cpu_count() or 1
-    return {"value": evals / dt / epp, "unit": UNIT, "cores": cores, "kind": pipe.kind,
+    return {"value": evals / dt / epp, "unit": UNIT, "cores": cores, "kind": pipe.kind, "variants": variants,
             "sample": "%.0f s of %s + torch-CPU fp32 net (TensorFlow absent), %d-visit searches, buffer 128 / 256 threads: "
                       "%.0f leaf-evals/s / %.0f evals per played move (measured on the reference search core)"
                       % (dt, "oracle/_ref/self_play_client.so" if pipe.kind == "reference" else "oracle C port", visits,
@@ -432,7 +444,8 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pool.close()
         try:
-            line["cpu_baseline"] = reference_sample(args.cpu_seconds, visits)
+            line["cpu_baseline"] = reference_sample(args.cpu_seconds, visits,
+                                                    gpu_evaluator=lambda f: net.forward(ctx, f, net.BF16))
             # second metric of BASELINE.json: the reference's own movegen/makemove (oracle/_ref/perft_ref) on the host cores
             from oracle import cpu as ocpu
             if os.path.exists(ocpu.REF_PERFT):
