@@ -284,7 +284,19 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        azdist.init("nccl")                   # counters only: the games themselves never cross ranks
+        # NCCL may print its version banner on stdout while the communicator comes up; stdout carries only the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            azdist.init("nccl")               # counters only: the games themselves never cross ranks
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
