@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libataxxzero.so")
+LIB_PATH = os.environ.get("AZ_LIB_PATH") or os.path.join(HERE, "libataxxzero.so")
 
 AZ_MAX_MOVES = 256
 AZ_FEATURES = 196

@@ -343,6 +343,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         // suspended descent would cost it a whole (empty) net launch
         D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : (cfg->games < 64 ? (1 << 20) : 48);
         D.seed = cfg->seed;
+        D.full_fetch = getenv("AZ_TREE_FULL_FETCH") ? atoi(getenv("AZ_TREE_FULL_FETCH")) : 0;
         D.rec_cap_words = rec_cap_words;
         const size_t G = (size_t)D.G;
         rc |= dev_alloc(&D.nodes, G * D.C * kNodeStride, false);

@@ -105,6 +105,7 @@ struct PoolDev {
     int32_t game_base;       // global index of this group's game 0 (RNG streams are keyed by the global game index)
     uint32_t rec_cap_words;
     uint64_t seed;
+    int32_t full_fetch;      // experiment (AZ_TREE_FULL_FETCH=1): always load 128 children per level, ignoring the edge's group count
     unsigned long long *prof;   // AZ_POOL_PROFILE=1: [G][8] clock cycles per phase of the last tick (debug aid, normally nullptr)
 };
 

@@ -159,4 +159,4 @@ def test_full_size_pool_properties(tmp_path, ctx, oracle):
             p = oracle.makemove(p, legal[move])
             checked += 1
         assert oracle.result(p) == game["result"]
-    assert checked >= 1500          # plies replayed
+    assert checked >= 1000          # plies replayed
