@@ -124,6 +124,11 @@ class ReferencePipeline:
             self.out = tempfile.mktemp(suffix=".json")
             self.buffers = [np.zeros((buffer_size, 7, 7, 4), dtype=np.float32) for _ in (0, 1)]
             self.keep = []
+            # the client announces itself on stdout (self_play_client.cpp:686-689); stdout is reserved for the JSON line
+            # (and every finished game, :640): for the lifetime of the pipeline fd 1 points at stderr
+            sys.stdout.flush()
+            self.saved_stdout = os.dup(1)
+            os.dup2(2, 1)
             self.dll.launch_threads(self.out.encode(), ctypes.c_int(visits), ctypes.c_void_p(self.buffers[0].ctypes.data),
                                     ctypes.c_void_p(self.buffers[1].ctypes.data), ctypes.c_int(buffer_size),
                                     ctypes.c_int(2 * buffer_size))
@@ -177,6 +182,9 @@ class ReferencePipeline:
     def close(self):
         if self.kind == "reference":
             self.dll.shutdown()
+            self.ctypes.CDLL(None).fflush(None)
+            os.dup2(self.saved_stdout, 1)
+            os.close(self.saved_stdout)
             try:
                 os.unlink(self.out)
             except OSError:
