@@ -32,7 +32,6 @@ constexpr int KG = F / 8;                // 16 k-groups of 8 channels
 constexpr int TILE_M = 128;              // GEMM rows per tile (2 boards x 64)
 constexpr int MARGIN = 16;               // zero rows before/after the tiles (shifts reach +-9)
 constexpr int ROW_BYTES = 16;            // 8 bf16
-constexpr int STAGES = 4;
 constexpr int STAGE_BYTES = 8 * F * ROW_BYTES;                 // 8 k-groups x 128 cout x 16 B = 16384
 constexpr int CHUNKS = 18;               // per layer: 2 input-channel halves x 9 taps
 constexpr int W_LBO = F * ROW_BYTES;     // 2048: bytes between k-groups of the B operand
@@ -48,6 +47,7 @@ constexpr int HEAD_LBO = HEAD_N * ROW_BYTES;
 template <int TILES>
 struct Cfg {
     static constexpr int UNIT_BOARDS = 2 * TILES;
+    static constexpr int STAGES = TILES == 1 ? 4 : 8;              // 16-KiB weight stages in flight (all the shared memory there is)
     static constexpr int ACT_ROWS = MARGIN + TILES * TILE_M + MARGIN;
     static constexpr int ACT_LBO = ACT_ROWS * ROW_BYTES;           // bytes between k-groups of the A operand
     static constexpr int ACT_BYTES = KG * ACT_LBO;
@@ -60,7 +60,7 @@ struct Cfg {
     static constexpr int OFF_SHIFT = OFF_RING + STAGES * STAGE_BYTES;   // float[TILES][2][F]: per-layer BN shifts, double-buffered
     static constexpr int OFF_VPART = OFF_SHIFT + TILES * 2 * F * 4;
     static constexpr int OFF_BAR = OFF_VPART + 64;
-    static constexpr int NUM_BARS = 2 * STAGES + 2 * TILES + 1;    // full/empty ring, acc_full/act_ready per tile, input staged
+    static constexpr int NUM_BARS = 2 * STAGES + 3 * TILES + 1;    // full/empty ring, acc_full + 2 x act_ready (channel halves) per tile, input staged
     static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
     static constexpr int SMEM_BYTES = OFF_TMEM + 16;
     static constexpr int NUM_WARPS = 2 + 4 * TILES;
@@ -288,7 +288,9 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto bar = [&](int i) { return sbase + C::OFF_BAR + 8 * i; };
     // barrier indices
-    constexpr int B_FULL = 0, B_EMPTY = STAGES, B_ACC = 2 * STAGES, B_ACT = 2 * STAGES + TILES, B_IN = 2 * STAGES + 2 * TILES;
+    constexpr int STAGES = C::STAGES;
+    // B_ACT + 2*tile + h: channels [64h, 64h+64) of the tile's new activations are in shared memory
+    constexpr int B_FULL = 0, B_EMPTY = STAGES, B_ACC = 2 * STAGES, B_ACT = 2 * STAGES + TILES, B_IN = 2 * STAGES + 3 * TILES;
 
     const int n_boards = P.n_ptr ? min(*P.n_ptr, P.n) : P.n;
     const int num_units = ((n_boards + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS + CS - 1) / CS * CS;   // cluster peers run the same number of passes
@@ -301,7 +303,11 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
     for (int i = threadIdx.x; i < C::ACT_BYTES / 16; i += C::NUM_THREADS) reinterpret_cast<uint4 *>(smem + C::OFF_ACT)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), CS); }
-        for (int t = 0; t < TILES; ++t) { mbar_init(bar(B_ACC + t), 1); mbar_init(bar(B_ACT + t), 128); }
+        for (int t = 0; t < TILES; ++t) {
+            mbar_init(bar(B_ACC + t), 1);
+            mbar_init(bar(B_ACT + 2 * t), 128);
+            mbar_init(bar(B_ACT + 2 * t + 1), 128);
+        }
         mbar_init(bar(B_IN), 128 * TILES);
         fence_barrier_init();
     }
@@ -336,10 +342,7 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
                 push(P.w_stream, WIN_CHUNK0);
                 push(P.w_stream + WIN_CHUNK0, WIN_BYTES - WIN_CHUNK0);
-                // every tile walks a layer's 18 chunks on its own (tile 1 runs one layer-time behind tile 0, see the issuer)
-                for (int l = 0; l < nl; ++l)
-                    for (int t = 0; t < TILES; ++t)
-                        for (int c = 0; c < CHUNKS; ++c) push(tower + ((size_t)l * CHUNKS + c) * STAGE_BYTES, STAGE_BYTES);
+                for (int c = 0; c < nl * CHUNKS; ++c) push(tower + (size_t)c * STAGE_BYTES, STAGE_BYTES);
                 if (heads) push(head_w, WHEAD_BYTES);
             }
         }
@@ -387,40 +390,39 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                 constexpr uint32_t A_KSTEP = (2 * C::ACT_LBO) >> 4, B_KSTEP = (2 * W_LBO) >> 4, A_HALF = (8 * C::ACT_LBO) >> 4;
                 for (int l = 0; l < nl; ++l) {
                     // tower layer l is conv layer l+1.  The second conv of a block accumulates straight ON TOP of the
-                    // block's input (the fp32 residual stream kept in TMEM): the skip connection costs no TMEM read.
+                    // block's input (the fp32 residual stream kept in TMEM): the skip connection costs no TMEM read, and
+                    // consecutive layers never share an accumulator -- which is what lets a layer START on input channels
+                    // 0..63 (its first nine chunks) while the previous layer's epilogue is still producing channels 64..127.
                     const uint32_t onto_res = (uint32_t)(l & 1);
                     const uint32_t d_col = tmem_base + (onto_res ? C::TM_RES : C::TM_ACC);
-                    // Tiles take turns on the tensor pipe, a whole layer each: while tile t's 72 MMAs run, the epilogue
-                    // warps of the other tile drain its previous layer, so the pipe never waits for an epilogue.
 #pragma unroll 1
-                    for (int t = 0; t < TILES; ++t) {
-                        mbar_wait(bar(B_ACT + t), act_phase);
+                    for (int half = 0; half < 2; ++half) {
+                        for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + 2 * t + half), act_phase);
                         tc_fence_after();
-#pragma unroll 1
-                        for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const int s = it % STAGES;
-                                mbar_wait(bar(B_FULL + s), (it / STAGES) & 1);
-                                tc_fence_after();
-                                const uint32_t b_lo = b_lo0 + s * (STAGE_BYTES >> 4);
-                                // tap shift in rows == shift in 16-byte units of the start-address field
-                                const uint32_t a_lo = a_lo0 + t * TILE_M + half * A_HALF + (uint32_t)((tap / 3 - 1) * 8 + (tap % 3 - 1));
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int s = it % STAGES;
+                            mbar_wait(bar(B_FULL + s), (it / STAGES) & 1);
+                            tc_fence_after();
+                            const uint32_t b_lo = b_lo0 + s * (STAGE_BYTES >> 4);
+                            // tap shift in rows == shift in 16-byte units of the start-address field
+                            const uint32_t a_lo = a_lo0 + half * A_HALF + (uint32_t)((tap / 3 - 1) * 8 + (tap % 3 - 1));
+#pragma unroll
+                            for (int t = 0; t < TILES; ++t) {           // every weight stage feeds all of the CTA's tiles
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
-                                    if (!(P.experiment & 2) || (half | tap | j) == 0)
-                                    umma_lo(d_col + t * 128, a_lo + j * A_KSTEP, a_hi, b_lo + j * B_KSTEP, b_hi, IDESC_128,
+                                    umma_lo(d_col + t * 128, a_lo + t * TILE_M + j * A_KSTEP, a_hi, b_lo + j * B_KSTEP, b_hi, IDESC_128,
                                             onto_res | (uint32_t)((half | tap | j) != 0));
                                 if (half == 1 && tap == 8) umma_commit(bar(B_ACC + t));
-                                free_stage(s);
-                                ++it;
                             }
+                            free_stage(s);
+                            ++it;
                         }
                     }
                     act_phase ^= 1;
                 }
                 // ---- heads: [128 rows x 128 ch] x [128 ch x 32] ----
-                for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + t), act_phase);
+                for (int t = 0; t < TILES; ++t) { mbar_wait(bar(B_ACT + 2 * t), act_phase); mbar_wait(bar(B_ACT + 2 * t + 1), act_phase); }
                 act_phase ^= 1;
                 tc_fence_after();
                 if (heads) {
@@ -514,11 +516,19 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                         float *dst = P.debug_act + ((size_t)board * 49 + cell) * F + q * 32;
                         for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(a[i]);
                     }
+                    if (q == 1 && l > 0) {
+                        // channels 0..63 of this row are in shared memory: the next layer may start on them.  Not after the
+                        // input conv: layer 1 reuses the accumulator this epilogue is still reading.
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive(bar(B_ACT + 2 * tile));
+                    }
                 }
                 if (writes_res) tmem_wait_st();
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(bar(B_ACT + tile));
+                if (l == 0) mbar_arrive(bar(B_ACT + 2 * tile));
+                mbar_arrive(bar(B_ACT + 2 * tile + 1));
             }
             if (heads) {
                 mbar_wait(bar(B_ACC + tile), acc_phase);
