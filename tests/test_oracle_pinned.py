@@ -289,3 +289,18 @@ def test_weight_file_layout_roundtrip(tmp_path):
     conv2, bn2 = net_numpy.load_model(str(tmp_path / "n.npy"))      # and the other way round
     assert all(np.array_equal(x, y) for x, y in zip(conv, conv2)) and all(np.array_equal(x, y) for x, y in zip(bn, bn2))
     assert a.packed().size == 3545906 + 50 * 128
+
+
+def test_live_reference_edge_positions(oracle, reference):
+    """Hand-made corner cases (zero pieces, stuck sides, full boards, walled-in pieces, 103 legal moves, jump-only
+    positions): the oracle and the compiled reference agree on move lists, adjudication and move application."""
+    from test_rules_gpu import EDGE_FENS
+    for fen in EDGE_FENS:
+        p = oracle.set_board(fen)
+        assert reference.set_board(fen).key() == p.key()
+        mo = oracle.movegen(p)
+        assert mo == reference.movegen(p), fen
+        assert oracle.result(p) == reference.result(p), fen
+        if oracle.result(p) == 0:
+            for m in mo:
+                assert oracle.makemove(p, m).key() == reference.makemove(p, m).key(), (fen, m)

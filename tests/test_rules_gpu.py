@@ -135,3 +135,47 @@ def test_random_playouts_on_device(ctx, oracle):
         first = np.bincount(plies["move"][:, 0], minlength=1)            # 16 legal first moves, each drawn ~1/16 of the time
         assert (first > 0).sum() == 16 and first[first > 0].min() > 600 / 16 * 0.4
     assert len(rules.random_playouts(ctx, rules.set_board(OPEN_FEN), 0)[1]) == 0
+
+
+EDGE_FENS = [
+    "7/7/7/3x3/7/7/7 x",                    # o has no pieces at all: x wins (x to move, 24 moves available)
+    "7/7/7/3x3/7/7/7 o",                    # ... also when the piece-less side is to move
+    "7/7/7/3o3/7/7/7 x",                    # the side to move has no pieces
+    "xxxxxxx/xxxxxxx/xxxxxxx/xxxxxxx/xxxxxxx/xxxxxxx/xxxxxx1 o",      # o has no pieces, one empty cell
+    "xxxxxxx/xxxxxxx/xxxxxxx/ooooooo/ooooooo/ooooooo/oooooo1 x",      # x cannot reach the last empty cell: stuck, o is credited
+    "xxxxxxx/xxxxxxx/xxxxxxx/xxxoooo/ooooooo/ooooooo/ooooooo x",      # full board: piece count decides (24 : 25)
+    "xxxxxxx/xxxxxxx/xxxxxxx/xxxxooo/ooooooo/ooooooo/ooooooo o",      # full board: 25 : 24
+    "xoo4/ooo4/ooo4/7/7/7/7 x",             # x walled in by enemy pieces: stuck, the opponent is credited every empty cell
+    "x-1o3/--5/7/7/7/7/7 x",                # blockers next to x: only jumps remain
+    "x1x1x1x/7/x1x1x1x/7/x1x1x1x/7/x1x1x1o x",   # very many moves for x (jumps + clones)
+    "7/7/2ooo2/2oxo2/2ooo2/7/7 x",          # only jumps available to x
+    "x5o/7/3-3/2-1-2/3-3/7/o5x o",          # the C++ start position with o to move
+    "-------/-------/-------/--xx---/-------/-------/------o x",     # blockers everywhere: nobody can move, counts decide
+]
+
+
+def test_edge_positions_vs_oracle_and_reference(ctx, oracle):
+    """Adjudication and move generation on hand-made corner cases (zero pieces, stuck sides, full boards, walled-in
+    pieces, maximum fan-out, jump-only positions) against the oracle and, when present, the compiled reference."""
+    from ataxxzero_b200 import rules
+    from oracle.cpu import Reference
+    ref = Reference() if Reference.available() else None
+    positions = [rules.set_board(f) for f in EDGE_FENS]
+    got_moves = rules.movegen_batch(ctx, positions)
+    got_res = rules.result_batch(ctx, positions)
+    feats = rules.features_batch(ctx, positions)
+    fan = 0
+    for fen, p, mv, res, f in zip(EDGE_FENS, positions, got_moves, got_res, feats):
+        op = oracle.set_board(fen)
+        assert mv == oracle.movegen(op), fen
+        assert int(res) == oracle.result(op), fen
+        assert np.array_equal(f.reshape(-1), np.asarray(oracle.features(op), dtype=np.float32).reshape(-1)), fen
+        if ref is not None:
+            assert mv == ref.movegen(op) and int(res) == ref.result(op), fen
+        fan = max(fan, len(mv))
+        if mv and int(res) == 0:            # every move applies identically
+            nxt = rules.makemove_batch(ctx, [p] * len(mv), mv)
+            for q, m in zip(rules.array_to_positions(nxt), mv):
+                assert q.key() == oracle.makemove(op, m).key(), (fen, m)
+    assert fan >= 100
+    assert [int(r) for r in got_res[:8]] == [1, 1, 2, 1, 2, 2, 1, 2]
