@@ -149,3 +149,46 @@ def test_play_errors_and_rebuild(ctx, oracle):
         tree.play(unvisited[0])
         tree.search(30)
         assert pool.root(0)["visits"] == [d[1] for d in tree.dist()]
+
+
+def test_endgame_and_degenerate_roots_vs_oracle(ctx, oracle):
+    """Roots where the tree is mostly adjudicated leaves (late endgames), roots with a single legal move, and roots that are
+    already decided: visits, edge scores and evaluation counts against the oracle's sequential search."""
+    import random
+    from ataxxzero_b200 import rules, search
+    from test_rules_gpu import EDGE_FENS
+    rng = random.Random(9)
+    roots = []
+    while len(roots) < 40:                                      # late endgames: few empty cells left
+        p = oracle.set_board(rules.START_FEN)
+        for _ in range(rng.randrange(150, 230)):
+            mv = oracle.movegen(p)
+            if not mv or oracle.result(p):
+                break
+            q = oracle.makemove(p, rng.choice(mv))
+            if oracle.result(q):
+                break
+            p = q
+        if oracle.result(p) == 0 and oracle.movegen(p):
+            roots.append(p)
+    roots += [oracle.set_board(f) for f in EDGE_FENS]           # includes decided positions and a 103-move root
+    with search.Pool(ctx, len(roots), 300, eval_mode=search.EVAL_EXTERNAL) as pool:
+        for i, p in enumerate(roots):
+            q = rules.Position()
+            q.ply, q.turn, q.blockers = p.ply, p.turn, p.blockers
+            q.pieces[0], q.pieces[1] = p.pieces[0], p.pieces[1]
+            pool.set_root(i, q)
+        pool.run_external(lambda feats: oracle.probe_eval(feats))
+        terminal_steps = pool.stats()["terminal_steps"]
+        for i, p in enumerate(roots):
+            r = pool.root(i)
+            if oracle.result(p) != 0:
+                assert r["moves"] == [] and r["root_visits"] == 0
+                continue
+            tree = oracle.tree(p, "probe")
+            tree.search(300)
+            want = tree.dist()
+            assert r["visits"] == [w[1] for w in want], i
+            assert [float(x).hex() for x in r["total_score"]] == [float(w[2]).hex() for w in want], i
+            tree.close()
+    assert terminal_steps > 1000                                # the adjudicated-leaf path really was exercised
