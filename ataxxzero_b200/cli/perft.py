@@ -27,6 +27,19 @@ def main(argv=None):
     ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args(argv)
     board = ataxx_rules.AtaxxState.from_fen(args.fen)
+    from .. import dist
+    rank, local_rank, world = dist.init()
+    if world > 1:                              # torchrun: root-split over the ranks, one all-reduce of the count
+        with Context(device=local_rank) as ctx:
+            t0 = time.perf_counter()
+            total = dist.perft_sharded(ctx, board.to_position(), args.depth)
+            dt = time.perf_counter() - t0
+        if rank == 0:
+            print("Total:", total)
+            print("(%d GPUs, %.3f s incl. communicator start-up, %.1f Mnodes/s)" % (world, dt, total / dt / 1e6))
+        import torch.distributed as torch_dist
+        torch_dist.destroy_process_group()
+        return total
     with Context(device=args.device) as ctx:
         t0 = time.perf_counter()
         total = 0

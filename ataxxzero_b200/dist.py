@@ -105,3 +105,26 @@ def gather_records(local_path, merged_path):
                 f.write(parts[r][:n].cpu().numpy().tobytes())
                 total += n
     return total
+
+
+def perft_sharded(ctx, root, depth):
+    """perft over all ranks: the depth-2 frontier (256 sub-trees from the opening) is dealt round-robin to the
+    ranks, each counts its share on its own GPU, one all-reduce(sum) of the uint64 total.  Any world size, also 1."""
+    import numpy as np
+    from . import rules
+    rank, _, world = env_rank()
+    if depth < 3:
+        return rules.perft(ctx, root, depth)
+    frontier = [root]
+    for _ in range(2):
+        moves = rules.movegen_batch(ctx, frontier)
+        parents = [p for p, mv in zip(frontier, moves) for _ in mv]
+        flat = [m for mv in moves for m in mv]
+        if not flat:
+            return 0
+        frontier = rules.array_to_positions(rules.makemove_batch(ctx, parents, flat))
+    mine = frontier[rank::world]
+    total = int(rules.perft_batch(ctx, mine, depth - 2).sum()) if mine else 0
+    # two 32-bit halves as float64 sums stay exact (each < 2^53) on both NCCL and gloo
+    parts = allreduce_stats({"lo": float(total & 0xffffffff), "hi": float(total >> 32)})
+    return (int(parts["hi"]) << 32) + int(parts["lo"])

@@ -162,3 +162,10 @@ def test_accelerated_generate_games_and_looper(tmp_path, engine_mod, oracle):
     for ln in lines:
         replay_and_check(oracle, ln, 24)
     assert "Training is out of scope" in r.stdout
+
+
+def test_perft_sharded_single_rank(ctx):
+    """dist.perft_sharded with one rank equals the plain device perft (the N>1 path is the same code plus one all-reduce)."""
+    from ataxxzero_b200 import dist, rules
+    for fen, depth, want in ((rules.OPEN_FEN, 5, 4752668), (rules.START_FEN, 6, 97538324), (rules.OPEN_FEN, 2, 256)):
+        assert dist.perft_sharded(ctx, rules.set_board(fen), depth) == want
