@@ -168,3 +168,31 @@ def test_generate_games_supervised_with_a_scripted_uai_engine(tmp_path):
             assert mv in board.legal_moves()
             board.move(mv)
         assert board.result() == game["result"]
+
+
+def test_uai_ringmaster_between_scripted_engines(tmp_path):
+    """uai_ringmaster.py flags and flow (pairings both ways round, PGN append, win tally) with two scripted engines."""
+    import sys
+    from conftest import ROOT
+    from ataxxzero_b200.cli import uai_ringmaster
+    script = tmp_path / "fake_uai.py"
+    script.write_text(
+        "import sys, random\n"
+        "sys.path.insert(0, %r)\n"
+        "from ataxxzero_b200 import ataxx_rules\n"
+        "from ataxxzero_b200.cli.uai_interface import uai_encode_move\n"
+        "board, rng = ataxx_rules.AtaxxState.initial(), random.Random(int(sys.argv[1]))\n"
+        "for line in sys.stdin:\n"
+        "    line = line.strip()\n"
+        "    if line == 'quit': break\n"
+        "    if line.startswith('position fen '): board = ataxx_rules.AtaxxState.from_fen(line[13:])\n"
+        "    elif line.startswith('go '): print('bestmove ' + uai_encode_move(rng.choice(board.legal_moves())))\n"
+        "    sys.stdout.flush()\n" % ROOT)
+    pgn = tmp_path / "games.pgn"
+    wins = uai_ringmaster.main(["--engine", "%s %s 1" % (sys.executable, script), "--engine", "%s %s 2" % (sys.executable, script),
+                                "--tc", "0.001", "--games", "2", "--pgn-out", str(pgn), "--opening", "f2, a2"])
+    assert sum(wins.values()) == 2
+    text = pgn.read_text()
+    assert text.count('[Result "') == 2 and text.count('[Opening "f2, a2"]') == 2 and '[TimeControl "+0.001"]' in text
+    first_line = [l for l in text.splitlines() if l and not l.startswith("[")][0]
+    assert first_line.startswith("f2 a2 ")
