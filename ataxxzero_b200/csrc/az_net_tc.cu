@@ -32,12 +32,25 @@ constexpr int KG = F / 8;                // 16 k-groups of 8 channels
 constexpr int TILE_M = 128;              // GEMM rows per tile (2 boards x 64)
 constexpr int MARGIN = 16;               // zero rows before/after the tiles (shifts reach +-9)
 constexpr int ROW_BYTES = 16;            // 8 bf16
-constexpr int STAGE_BYTES = 8 * F * ROW_BYTES;                 // 8 k-groups x 128 cout x 16 B = 16384
-constexpr int CHUNKS = 18;               // per layer: 2 input-channel halves x 9 taps
+#ifndef AZ_NET_SPLIT
+#define AZ_NET_SPLIT 2
+#endif
+// A layer's weights travel as SPLIT x 9 chunks: input-channel part (128 / SPLIT channels) major, tap minor.  A layer can start
+// on part p as soon as the previous epilogue has produced that part's channels, so SPLIT sets how early the MMAs -- and with
+// them the weight stream -- restart after a layer (SPLIT = 2: half way through the epilogue, 4: after its first quarter).
+// Measured (B200, 2048 games x 800 visits): SPLIT 2 -> 0.507 ms per net launch, SPLIT 4 -> 0.541 ms (8-KiB stages double the
+// per-stage hand-offs of the single issuing thread); the 2-tile variant is indifferent (0.517 / 0.516 ms).
+constexpr int SPLIT = AZ_NET_SPLIT;
+constexpr int PART_KG = KG / SPLIT;      // k-groups (of 8 channels) per chunk
+constexpr int PART_MMAS = PART_KG / 2;   // K = 16 steps per chunk
+constexpr int STAGE_BYTES = PART_KG * F * ROW_BYTES;           // one tap x 128/SPLIT input channels x 128 cout (SPLIT 4: 8 KiB)
+constexpr int CHUNKS = SPLIT * 9;
+static_assert(SPLIT == 2 || SPLIT == 4, "input channels per chunk: 64 or 32");
 constexpr int W_LBO = F * ROW_BYTES;     // 2048: bytes between k-groups of the B operand
 constexpr int ZERO_BYTES = TILE_M * ROW_BYTES;                 // zero k-group for the padded 10th tap
 constexpr int WIN_BYTES = 5 * 2 * F * ROW_BYTES;               // input conv: 5 k-steps x 2 k-groups x 128 cout = 20480
-constexpr int WIN_CHUNK0 = 4 * 2 * F * ROW_BYTES;              // k-steps 0..3 travel as one stage, k-step 4 as a second
+constexpr int WIN_KSTEP_BYTES = 2 * F * ROW_BYTES;             // one K = 16 step of the input conv (two taps): 4 KiB
+constexpr int WIN_KSTEPS_PER_STAGE = STAGE_BYTES / WIN_KSTEP_BYTES;     // the 5 k-steps travel in stages of this many
 constexpr int HEAD_N = 32;               // 17 policy planes + 1 value plane, padded to a legal UMMA N
 constexpr int WHEAD_BYTES = KG * HEAD_N * ROW_BYTES;           // 8192
 constexpr int HEAD_LBO = HEAD_N * ROW_BYTES;
@@ -47,7 +60,7 @@ constexpr int HEAD_LBO = HEAD_N * ROW_BYTES;
 template <int TILES>
 struct Cfg {
     static constexpr int UNIT_BOARDS = 2 * TILES;
-    static constexpr int STAGES = TILES == 1 ? 4 : 8;              // 16-KiB weight stages in flight (all the shared memory there is)
+    static constexpr int STAGES = (TILES == 1 ? 4 : 8) * (16384 / STAGE_BYTES);   // 64 / 128 KiB of weight stages in flight
     static constexpr int ACT_ROWS = MARGIN + TILES * TILE_M + MARGIN;
     static constexpr int ACT_LBO = ACT_ROWS * ROW_BYTES;           // bytes between k-groups of the A operand
     static constexpr int ACT_BYTES = KG * ACT_LBO;
@@ -60,7 +73,7 @@ struct Cfg {
     static constexpr int OFF_SHIFT = OFF_RING + STAGES * STAGE_BYTES;   // float[TILES][2][F]: per-layer BN shifts, double-buffered
     static constexpr int OFF_VPART = OFF_SHIFT + TILES * 2 * F * 4;
     static constexpr int OFF_BAR = OFF_VPART + 64;
-    static constexpr int NUM_BARS = 2 * STAGES + 3 * TILES + 1;    // full/empty ring, acc_full + 2 x act_ready (channel halves) per tile, input staged
+    static constexpr int NUM_BARS = 2 * STAGES + (1 + SPLIT) * TILES + 1;   // full/empty ring, acc_full + SPLIT x act_ready per tile, input staged
     static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
     static constexpr int SMEM_BYTES = OFF_TMEM + 16;
     static constexpr int NUM_WARPS = 2 + 4 * TILES;
@@ -289,8 +302,8 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
     auto bar = [&](int i) { return sbase + C::OFF_BAR + 8 * i; };
     // barrier indices
     constexpr int STAGES = C::STAGES;
-    // B_ACT + 2*tile + h: channels [64h, 64h+64) of the tile's new activations are in shared memory
-    constexpr int B_FULL = 0, B_EMPTY = STAGES, B_ACC = 2 * STAGES, B_ACT = 2 * STAGES + TILES, B_IN = 2 * STAGES + 3 * TILES;
+    // B_ACT + SPLIT*tile + p: channels [128/SPLIT * p, 128/SPLIT * (p+1)) of the tile's new activations are in shared memory
+    constexpr int B_FULL = 0, B_EMPTY = STAGES, B_ACC = 2 * STAGES, B_ACT = 2 * STAGES + TILES, B_IN = 2 * STAGES + (1 + SPLIT) * TILES;
 
     const int n_boards = P.n_ptr ? min(*P.n_ptr, P.n) : P.n;
     const int num_units = ((n_boards + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS + CS - 1) / CS * CS;   // cluster peers run the same number of passes
@@ -305,8 +318,7 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), CS); }
         for (int t = 0; t < TILES; ++t) {
             mbar_init(bar(B_ACC + t), 1);
-            mbar_init(bar(B_ACT + 2 * t), 128);
-            mbar_init(bar(B_ACT + 2 * t + 1), 128);
+            for (int p = 0; p < SPLIT; ++p) mbar_init(bar(B_ACT + SPLIT * t + p), 128);
         }
         mbar_init(bar(B_IN), 128 * TILES);
         fence_barrier_init();
@@ -340,8 +352,8 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
             const uint8_t *tower = P.w_stream + WIN_BYTES;
             const uint8_t *head_w = tower + (size_t)tower_layers * CHUNKS * STAGE_BYTES;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                push(P.w_stream, WIN_CHUNK0);
-                push(P.w_stream + WIN_CHUNK0, WIN_BYTES - WIN_CHUNK0);
+                for (int j0 = 0; j0 < 5; j0 += WIN_KSTEPS_PER_STAGE)
+                    push(P.w_stream + j0 * WIN_KSTEP_BYTES, min(WIN_KSTEPS_PER_STAGE, 5 - j0) * WIN_KSTEP_BYTES);
                 for (int c = 0; c < nl * CHUNKS; ++c) push(tower + (size_t)c * STAGE_BYTES, STAGE_BYTES);
                 if (heads) push(head_w, WHEAD_BYTES);
             }
@@ -366,19 +378,20 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                 mbar_wait(bar(B_IN), in_phase);
                 in_phase ^= 1;
                 tc_fence_after();
-                for (int part = 0; part < 2; ++part) {
+                for (int j0 = 0; j0 < 5; j0 += WIN_KSTEPS_PER_STAGE) {
                     const uint32_t b_rows = acquire();
+                    const int j1 = min(j0 + WIN_KSTEPS_PER_STAGE, 5);
                     for (int t = 0; t < TILES; ++t) {
                         const uint32_t in_rows = sbase + C::OFF_IN + (MARGIN + t * TILE_M) * ROW_BYTES;
-                        for (int j = part * 4; j < (part ? 5 : 4); ++j) {
+                        for (int j = j0; j < j1; ++j) {
                             const int tap0 = 2 * j, tap1 = 2 * j + 1;
                             const uint32_t a0 = in_rows + ((tap0 / 3 - 1) * 8 + (tap0 % 3 - 1)) * ROW_BYTES;
                             // the 10th "tap" has all-zero weights: any finite rows will do, take the next row
                             const uint32_t a1 = tap1 < 9 ? in_rows + ((tap1 / 3 - 1) * 8 + (tap1 % 3 - 1)) * ROW_BYTES : a0 + ROW_BYTES;
-                            umma(tmem_base + C::TM_ACC + t * 128, make_desc(a0, a1 - a0), make_desc(b_rows + (j - part * 4) * 2 * W_LBO, W_LBO),
+                            umma(tmem_base + C::TM_ACC + t * 128, make_desc(a0, a1 - a0), make_desc(b_rows + (j - j0) * 2 * W_LBO, W_LBO),
                                  IDESC_128, j > 0);
                         }
-                        if (part) umma_commit(bar(B_ACC + t));
+                        if (j1 == 5) umma_commit(bar(B_ACC + t));
                     }
                     release();
                 }
@@ -387,17 +400,17 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                 const uint32_t a_hi = (uint32_t)(make_desc(0, C::ACT_LBO) >> 32), b_hi = (uint32_t)(make_desc(0, W_LBO) >> 32);
                 const uint32_t a_lo0 = (uint32_t)make_desc(sbase + C::OFF_ACT + MARGIN * ROW_BYTES, C::ACT_LBO);
                 const uint32_t b_lo0 = (uint32_t)make_desc(sbase + C::OFF_RING, W_LBO);
-                constexpr uint32_t A_KSTEP = (2 * C::ACT_LBO) >> 4, B_KSTEP = (2 * W_LBO) >> 4, A_HALF = (8 * C::ACT_LBO) >> 4;
+                constexpr uint32_t A_KSTEP = (2 * C::ACT_LBO) >> 4, B_KSTEP = (2 * W_LBO) >> 4, A_PART = (PART_KG * C::ACT_LBO) >> 4;
                 for (int l = 0; l < nl; ++l) {
                     // tower layer l is conv layer l+1.  The second conv of a block accumulates straight ON TOP of the
                     // block's input (the fp32 residual stream kept in TMEM): the skip connection costs no TMEM read, and
-                    // consecutive layers never share an accumulator -- which is what lets a layer START on input channels
-                    // 0..63 (its first nine chunks) while the previous layer's epilogue is still producing channels 64..127.
+                    // consecutive layers never share an accumulator -- which is what lets a layer START on its first input-
+                    // channel part (its first nine chunks) while the previous layer's epilogue is still producing the rest.
                     const uint32_t onto_res = (uint32_t)(l & 1);
                     const uint32_t d_col = tmem_base + (onto_res ? C::TM_RES : C::TM_ACC);
 #pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
-                        for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + 2 * t + half), act_phase);
+                    for (int part = 0; part < SPLIT; ++part) {
+                        for (int t = 0; t < TILES; ++t) mbar_wait(bar(B_ACT + SPLIT * t + part), act_phase);
                         tc_fence_after();
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
@@ -406,14 +419,14 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                             tc_fence_after();
                             const uint32_t b_lo = b_lo0 + s * (STAGE_BYTES >> 4);
                             // tap shift in rows == shift in 16-byte units of the start-address field
-                            const uint32_t a_lo = a_lo0 + half * A_HALF + (uint32_t)((tap / 3 - 1) * 8 + (tap % 3 - 1));
+                            const uint32_t a_lo = a_lo0 + part * A_PART + (uint32_t)((tap / 3 - 1) * 8 + (tap % 3 - 1));
 #pragma unroll
                             for (int t = 0; t < TILES; ++t) {           // every weight stage feeds all of the CTA's tiles
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
+                                for (int j = 0; j < PART_MMAS; ++j)
                                     umma_lo(d_col + t * 128, a_lo + t * TILE_M + j * A_KSTEP, a_hi, b_lo + j * B_KSTEP, b_hi, IDESC_128,
-                                            onto_res | (uint32_t)((half | tap | j) != 0));
-                                if (half == 1 && tap == 8) umma_commit(bar(B_ACC + t));
+                                            onto_res | (uint32_t)((part | tap | j) != 0));
+                                if (part == SPLIT - 1 && tap == 8) umma_commit(bar(B_ACC + t));
                             }
                             free_stage(s);
                             ++it;
@@ -422,7 +435,8 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                     act_phase ^= 1;
                 }
                 // ---- heads: [128 rows x 128 ch] x [128 ch x 32] ----
-                for (int t = 0; t < TILES; ++t) { mbar_wait(bar(B_ACT + 2 * t), act_phase); mbar_wait(bar(B_ACT + 2 * t + 1), act_phase); }
+                for (int t = 0; t < TILES; ++t)
+                    for (int p = 0; p < SPLIT; ++p) mbar_wait(bar(B_ACT + SPLIT * t + p), act_phase);
                 act_phase ^= 1;
                 tc_fence_after();
                 if (heads) {
@@ -516,19 +530,20 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                         float *dst = P.debug_act + ((size_t)board * 49 + cell) * F + q * 32;
                         for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(a[i]);
                     }
-                    if (q == 1 && l > 0) {
-                        // channels 0..63 of this row are in shared memory: the next layer may start on them.  Not after the
+                    if (l > 0 && q < 3 && ((q + 1) % (4 / SPLIT)) == 0) {
+                        // a part of this row's channels is in shared memory: the next layer may start on it.  Not after the
                         // input conv: layer 1 reuses the accumulator this epilogue is still reading.
                         fence_proxy_async();
                         tc_fence_before();
-                        mbar_arrive(bar(B_ACT + 2 * tile));
+                        mbar_arrive(bar(B_ACT + SPLIT * tile + q / (4 / SPLIT)));
                     }
                 }
                 if (writes_res) tmem_wait_st();
                 fence_proxy_async();
                 tc_fence_before();
-                if (l == 0) mbar_arrive(bar(B_ACT + 2 * tile));
-                mbar_arrive(bar(B_ACT + 2 * tile + 1));
+                if (l == 0)
+                    for (int p = 0; p < SPLIT - 1; ++p) mbar_arrive(bar(B_ACT + SPLIT * tile + p));
+                mbar_arrive(bar(B_ACT + SPLIT * tile + SPLIT - 1));
             }
             if (heads) {
                 mbar_wait(bar(B_ACC + tile), acc_phase);
@@ -576,17 +591,18 @@ namespace {
 __global__ void k_tile_tower(const float *__restrict__ w_tower, const float *__restrict__ scale, int tower_layers,
                              __nv_bfloat16 *__restrict__ out)
 {
-    // out index: ((((l*18 + chunk)*8 + kg)*128 + co)*8 + i)
+    // out index: ((((l*CHUNKS + chunk)*PART_KG + kg)*128 + co)*8 + i), chunk = part*9 + tap
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)tower_layers * CHUNKS * 8 * F * 8;
+    const size_t total = (size_t)tower_layers * CHUNKS * PART_KG * F * 8;
     if (idx >= total) return;
     const int i = (int)(idx & 7);
     const int co = (int)((idx >> 3) & 127);
-    const int kg = (int)((idx >> 10) & 7);
-    const int chunk = (int)((idx >> 13) % CHUNKS);
-    const int l = (int)((idx >> 13) / CHUNKS);
-    const int half = chunk / 9, tap = chunk % 9;
-    const int cin = half * 64 + kg * 8 + i;
+    const size_t rest = idx >> 10;
+    const int kg = (int)(rest % PART_KG);
+    const int chunk = (int)((rest / PART_KG) % CHUNKS);
+    const int l = (int)(rest / PART_KG / CHUNKS);
+    const int part = chunk / 9, tap = chunk % 9;
+    const int cin = (part * PART_KG + kg) * 8 + i;
     const float w = w_tower[(((size_t)l * 9 + tap) * F + cin) * F + co] * scale[(size_t)(l + 1) * F + co];
     out[idx] = __float2bfloat16_rn(w);
 }
@@ -643,7 +659,7 @@ int az_net_tc_alloc(AzNet *net)
 int az_net_tc_prepare(az_context *ctx, AzNet *net)
 {
     cudaStream_t s = ctx->stream;
-    const size_t tower = (size_t)2 * net->blocks * CHUNKS * 8 * F * 8;
+    const size_t tower = (size_t)2 * net->blocks * CHUNKS * PART_KG * F * 8;
     k_tile_tower<<<(unsigned)((tower + 255) / 256), 256, 0, s>>>(net->w_tower, net->bn_scale, 2 * net->blocks, net->tc_w);
     const int small = std::max(std::max(5 * 2 * F * 8, KG * HEAD_N * 8), net->layers * F);
     k_tile_small<<<(small + 255) / 256, 256, 0, s>>>(net->w_in, net->w_policy, net->w_value, net->bn_raw, net->bn_scale, net->layers,
