@@ -23,12 +23,14 @@ void aztree_launch_set_roots(const PoolDev &P, const az_position *d_pos, cudaStr
 void aztree_launch_play(const PoolDev &P, int g, int move, int *d_status, cudaStream_t s);
 void aztree_launch_release(const PoolDev &P, const DoneEntry *d_done, int n, cudaStream_t s);
 void aztree_launch_features(const az_position *d_pos, int n, float *d_out, cudaStream_t s);
+void aztree_launch_gather(const PoolDev &P, const DoneEntry *d_done, const uint32_t *d_offsets, int n, uint32_t *d_out, cudaStream_t s);
+void aztree_launch_debug_gamma(double alpha, uint64_t seed, int n, double *d_out, cudaStream_t s);
+void aztree_launch_debug_sample(const int32_t *d_visits, int L, int N, uint64_t seed, int n, int32_t *d_out, cudaStream_t s);
 
-// A pool is split into GROUPS of games, each with its own tree memory, request batch and CUDA stream.  With two
-// groups the tree kernel of one group runs while the net kernel evaluates the other group's leaves: the net kernel
-// is tensor-pipe bound and leaves registers / shared memory / issue slots for the latency-bound tree warps, so
-// the tree time disappears behind the net time (self-play with the internal net only; search and external-
-// evaluator pools use one group on the context stream).
+// A pool is split into GROUPS of games, each with its own tree memory, request batch and CUDA stream.  One group on the
+// context stream is the default and the measured optimum.  More groups (AZ_POOL_GROUPS=2..4, self-play on the internal net
+// only) let the tree kernel of one group run under the net kernel of another; that overlap is opt-in because it measured
+// SLOWER on B200: a tree kernel that shares SMs with the net kernel's weight stream takes ~2.2x longer.
 const int kTicksPerDrain = 32;
 
 struct Group {
@@ -40,15 +42,19 @@ struct Group {
     int32_t *d_status = nullptr;
     float *d_features = nullptr;          // external mode: [G][196]
     DoneEntry *d_done_snapshot = nullptr; // copy of the done queue being drained
+    uint32_t *d_offsets = nullptr;        // [2G] word offset of every drained record in d_stage
+    uint32_t *d_stage = nullptr;          // finished records packed back to back (k_gather_records)
+    size_t stage_words = 0;
     // pinned host mirrors
     int32_t *h_counts = nullptr;          // [0] req_count, [1] busy_count, [2] status, [3] done_count
     DoneEntry *h_done = nullptr;          // [2G]
-    uint32_t *h_record = nullptr;         // one record buffer
+    uint32_t *h_offsets = nullptr;        // [2G]
+    uint32_t *h_stage = nullptr;          // [stage_words]
     std::vector<Game> h_games;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    // AZ_POOL_TRACE=1: events around every kernel of every tick (as scheduled, i.e. with the groups overlapping)
-    std::vector<cudaEvent_t> trace;       // [kTicksPerDrain][3]
-    double trace_tree_ms = 0, trace_net_ms = 0, trace_gap_ms = 0;
+    // CUDA events around the tree and the net kernel of EVERY tick between two drains: tree_seconds / net_seconds are sums
+    // of measured launches, not extrapolations
+    std::vector<cudaEvent_t> ev;          // [kTicksPerDrain][3]
+    double trace_gap_ms = 0;
     uint64_t trace_n = 0;
 };
 
@@ -180,7 +186,8 @@ std::string record_to_json(const uint32_t *rec, int words, int plies, int result
     return "{\"boards\":" + boards + "],\"dists\":" + dists + "],\"moves\":" + moves + "],\"result\":" + std::to_string(result) + "}";
 }
 
-// copy out a group's finished games, append them to `out` (may be null: records are dropped), release the buffers
+// Copy out a group's finished games, append them to `out` (may be null: records are dropped), release the buffers.
+// The records are packed into one staging buffer on the device and cross PCIe in ONE copy per drain.
 int drain_finished(az_pool *pool, Group &grp, FILE *out, int64_t *games_written, bool copy_payload = true)
 {
     cudaStream_t s = grp.stream;
@@ -192,22 +199,36 @@ int drain_finished(az_pool *pool, Group &grp, FILE *out, int64_t *games_written,
     AZ_CUDA(cudaMemcpyAsync(grp.d_done_snapshot, grp.dev.done, sizeof(DoneEntry) * n, cudaMemcpyDeviceToDevice, s));
     AZ_CUDA(cudaMemsetAsync(grp.dev.done_count, 0, sizeof(int32_t), s));
     AZ_CUDA(cudaStreamSynchronize(s));
-    for (int i = 0; i < n; ++i) {
-        const DoneEntry &d = grp.h_done[i];
-        const uint32_t *src = grp.dev.records + ((size_t)d.game * 2 + d.buf) * grp.dev.rec_cap_words;
-        if (copy_payload) {
-            AZ_CUDA(cudaMemcpyAsync(grp.h_record, src, sizeof(uint32_t) * d.words, cudaMemcpyDeviceToHost, s));
+    if (copy_payload) {
+        for (int first = 0; first < n;) {                 // normally one pass; more only if a drain exceeds the staging buffer
+            size_t words = 0;
+            int last = first;
+            while (last < n && words + (size_t)grp.h_done[last].words <= grp.stage_words) {
+                grp.h_offsets[last] = (uint32_t)words;
+                words += (size_t)grp.h_done[last].words;
+                ++last;
+            }
+            if (last == first) return az_fail(AZ_ERR_CAPACITY, "record of %d words exceeds the staging buffer", grp.h_done[first].words);
+            const int m = last - first;
+            AZ_CUDA(cudaMemcpyAsync(grp.d_offsets, grp.h_offsets + first, sizeof(uint32_t) * m, cudaMemcpyHostToDevice, s));
+            aztree_launch_gather(grp.dev, grp.d_done_snapshot + first, grp.d_offsets, m, grp.d_stage, s);
+            pool->launches++;
+            AZ_CUDA(cudaMemcpyAsync(grp.h_stage, grp.d_stage, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost, s));
             AZ_CUDA(cudaStreamSynchronize(s));
-            pool->d2h_bytes += sizeof(uint32_t) * (uint64_t)d.words;
+            pool->d2h_bytes += sizeof(uint32_t) * (uint64_t)words;
+            for (int i = first; i < last && out; ++i) {
+                const DoneEntry &d = grp.h_done[i];
+                const std::string line = record_to_json(grp.h_stage + grp.h_offsets[i], d.words, d.plies, d.result);
+                if (fwrite(line.data(), 1, line.size(), out) != line.size() || fputc('\n', out) == EOF)
+                    return az_fail(AZ_ERR_IO, "short write to the game file");
+            }
+            first = last;
         }
-        if (out && copy_payload) {
-            const std::string line = record_to_json(grp.h_record, d.words, d.plies, d.result);
-            if (fwrite(line.data(), 1, line.size(), out) != line.size() || fputc('\n', out) == EOF)
-                return az_fail(AZ_ERR_IO, "short write to the game file");
-            fflush(out);                                              // one flushed line per game (:641-642)
-        }
+        if (out) fflush(out);                             // whole lines only, flushed once per drain (:641-642 flushes per game)
+    }
+    for (int i = 0; i < n; ++i) {
         pool->written_games++;
-        pool->written_positions += d.plies;
+        pool->written_positions += grp.h_done[i].plies;
         if (games_written) (*games_written)++;
     }
     aztree_launch_release(grp.dev, grp.d_done_snapshot, n, s);
@@ -219,12 +240,13 @@ void free_group(Group &grp)
 {
     PoolDev &D = grp.dev;
     void *ptrs[] = {D.nodes, D.games, D.path, D.gstack, D.req_pos, D.req_game, D.req_count, D.logits, D.values, D.records,
-                    D.done, D.done_count, grp.d_done_snapshot, grp.d_status, grp.d_features};
+                    D.done, D.done_count, grp.d_done_snapshot, grp.d_status, grp.d_features, grp.d_offsets, grp.d_stage};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (grp.h_counts) cudaFreeHost(grp.h_counts);
     if (grp.h_done) cudaFreeHost(grp.h_done);
-    if (grp.h_record) cudaFreeHost(grp.h_record);
+    if (grp.h_offsets) cudaFreeHost(grp.h_offsets);
+    if (grp.h_stage) cudaFreeHost(grp.h_stage);
     for (auto &e : grp.ev)
         if (e) cudaEventDestroy(e);
     if (grp.own_stream && grp.stream) cudaStreamDestroy(grp.stream);
@@ -294,10 +316,12 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
             total += (int)v;
             p = *end == ',' ? end + 1 : end;
         }
-        if (!sizes.empty() && total == cfg->games && sizes.size() <= 4) {
-            pool->group_size = sizes;
-            n_groups = (int)sizes.size();
+        if (sizes.empty() || total != cfg->games || sizes.size() > 4) {
+            delete pool;
+            return az_fail(AZ_ERR_ARG, "az_pool_create: AZ_POOL_SPLIT='%s' must list 1..4 positive group sizes that sum to games=%d", split, cfg->games);
         }
+        pool->group_size = sizes;
+        n_groups = (int)sizes.size();
     }
     pool->groups.resize(n_groups);
 
@@ -343,7 +367,8 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         // suspended descent would cost it a whole (empty) net launch
         D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : (cfg->games < 64 ? (1 << 20) : 48);
         D.seed = cfg->seed;
-        D.full_fetch = getenv("AZ_TREE_FULL_FETCH") ? atoi(getenv("AZ_TREE_FULL_FETCH")) : 0;
+        D.tick_cycles = getenv("AZ_TICK_CYCLES") ? atoi(getenv("AZ_TICK_CYCLES")) : 0;
+        D.force_slow = getenv("AZ_TREE_FORCE_SLOW") ? atoi(getenv("AZ_TREE_FORCE_SLOW")) : 0;
         D.rec_cap_words = rec_cap_words;
         const size_t G = (size_t)D.G;
         rc |= dev_alloc(&D.nodes, G * D.C * kNodeStride, false);
@@ -359,12 +384,19 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         rc |= dev_alloc(&D.done, 2 * G);
         rc |= dev_alloc(&D.done_count, 1);
         rc |= dev_alloc(&grp.d_done_snapshot, 2 * G);
+        rc |= dev_alloc(&grp.d_offsets, 2 * G);
+        // staging for one drain: every game can hand over at most its two record buffers; in practice a drain carries a few
+        // dozen games, so the buffer is sized for 64 full-length records (a larger drain is fetched in several passes)
+        grp.stage_words = (size_t)D.rec_cap_words * (cfg->auto_play ? std::min<size_t>(2 * G, 64) : 1);
+        rc |= dev_alloc(&grp.d_stage, grp.stage_words, false);
         rc |= dev_alloc(&grp.d_status, 4);
         rc |= dev_alloc(&grp.d_features, G * AZ_FEATURES);
         if (rc) break;
         if (cudaMallocHost(&grp.h_counts, 16 * sizeof(int32_t)) != cudaSuccess || cudaMallocHost(&grp.h_done, sizeof(DoneEntry) * 2 * G) != cudaSuccess ||
-            cudaMallocHost(&grp.h_record, sizeof(uint32_t) * D.rec_cap_words) != cudaSuccess) { rc = az_fail(AZ_ERR_CUDA, "az_pool_create: pinned host alloc"); break; }
+            cudaMallocHost(&grp.h_offsets, sizeof(uint32_t) * 2 * G) != cudaSuccess ||
+            cudaMallocHost(&grp.h_stage, sizeof(uint32_t) * grp.stage_words) != cudaSuccess) { rc = az_fail(AZ_ERR_CUDA, "az_pool_create: pinned host alloc"); break; }
         grp.h_games.resize(G);
+        grp.ev.assign(3 * kTicksPerDrain, nullptr);
         for (auto &e : grp.ev)
             if (cudaEventCreate(&e) != cudaSuccess) rc = az_fail(AZ_ERR_CUDA, "az_pool_create: event");
         if (n_groups > 1) {
@@ -374,10 +406,6 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
             grp.stream = ctx->stream;
         }
         if (getenv("AZ_POOL_PROFILE")) rc |= dev_alloc(&D.prof, G * 8);
-        if (getenv("AZ_POOL_TRACE")) {
-            grp.trace.resize(3 * kTicksPerDrain);
-            for (auto &e : grp.trace) cudaEventCreate(&e);
-        }
         aztree_launch_init_all(D, start, grp.stream);
         pool->launches++;
     }
@@ -409,12 +437,9 @@ extern "C" void az_pool_destroy(az_pool *pool)
             cudaFree(grp.dev.prof);
             grp.dev.prof = nullptr;
         }
-        if (grp.trace_n)
-            fprintf(stderr, "[az_pool trace] group@%d: tree %.3f ms, net %.3f ms (launch to completion, overlapped), idle gap %.3f ms, %llu ticks\n",
-                    grp.first_game, grp.trace_tree_ms / grp.trace_n, grp.trace_net_ms / grp.trace_n, grp.trace_gap_ms / grp.trace_n,
-                    (unsigned long long)grp.trace_n);
-        for (auto &e : grp.trace) cudaEventDestroy(e);
-        grp.trace.clear();
+        if (grp.trace_n && getenv("AZ_POOL_TRACE"))
+            fprintf(stderr, "[az_pool trace] group@%d: idle gap between ticks %.4f ms (mean over %llu ticks)\n", grp.first_game,
+                    grp.trace_gap_ms / grp.trace_n, (unsigned long long)grp.trace_n);
         free_group(grp);
     }
     delete pool;
@@ -558,7 +583,7 @@ extern "C" int az_pool_collect(az_pool *pool, float *features, int32_t *n_reques
         for (int g = 0; g < grp.dev.G; ++g) busy |= grp.h_games[g].status == ST_IDLE || grp.h_games[g].status == ST_DESCEND;
         if (!busy) break;                       // every tree is waiting, done or stalled
     }
-    const int n = grp.h_counts[0];
+    const int n = std::min(grp.h_counts[0], grp.dev.cap);   // requests beyond the cap stay queued (the tree kernel re-issues them)
     if (n > 0) {
         aztree_launch_features(grp.dev.req_pos, n, grp.d_features, s);
         pool->launches++;
@@ -571,11 +596,12 @@ extern "C" int az_pool_collect(az_pool *pool, float *features, int32_t *n_reques
     return AZ_OK;
 }
 
-extern "C" int az_pool_provide(az_pool *pool, const float *logits, const float *values)
+extern "C" int az_pool_provide_n(az_pool *pool, const float *logits, const float *values, int32_t n_rows)
 {
     AZ_REQUIRE(pool && logits && values, AZ_ERR_ARG, "az_pool_provide: null argument");
     AZ_REQUIRE(pool->pending_requests > 0, AZ_ERR_STATE, "az_pool_provide: no outstanding requests");
     const int n = pool->pending_requests;
+    AZ_REQUIRE(n_rows == n, AZ_ERR_ARG, "az_pool_provide: %d evaluations handed in for %d outstanding requests", n_rows, n);
     Group &grp = pool->groups[0];
     cudaStream_t s = grp.stream;
     AZ_CUDA(cudaMemcpyAsync(grp.dev.logits, logits, sizeof(float) * AZ_LOGITS * n, cudaMemcpyHostToDevice, s));
@@ -583,6 +609,13 @@ extern "C" int az_pool_provide(az_pool *pool, const float *logits, const float *
     AZ_CUDA(cudaStreamSynchronize(s));      // the caller may free its arrays right away (complete_workload copies too)
     pool->pending_requests = 0;
     return AZ_OK;
+}
+
+// complete_workload() semantics: the caller's arrays are trusted to hold one row per outstanding request
+extern "C" int az_pool_provide(az_pool *pool, const float *logits, const float *values)
+{
+    AZ_REQUIRE(pool, AZ_ERR_ARG, "az_pool_provide: null argument");
+    return az_pool_provide_n(pool, logits, values, pool->pending_requests);
 }
 
 extern "C" int az_pool_root(az_pool *pool, int game, az_position *pos, int32_t *n_moves, az_move *moves, int32_t *visits,
@@ -612,9 +645,15 @@ extern "C" int az_pool_root(az_pool *pool, int game, az_position *pos, int32_t *
     if (root_value) *root_value = h->value;
     for (int i = 0; i < h->n_moves; ++i) {
         if (moves) moves[i] = reinterpret_cast<const uint16_t *>(slot.data() + kOffMove)[i];
-        if (visits) visits[i] = (int32_t)reinterpret_cast<const uint32_t *>(slot.data() + kOffN)[i];
-        if (total_score) total_score[i] = reinterpret_cast<const double *>(slot.data() + kOffW)[i];
+        if (visits) visits[i] = 0;
+        if (total_score) total_score[i] = 0.0;
         if (prior) prior[i] = reinterpret_cast<const double *>(slot.data() + kOffP)[i];
+    }
+    const Entry *ent = reinterpret_cast<const Entry *>(slot.data() + kOffEntry);
+    for (int e = 0; e < h->k; ++e) {                      // edges live in a dense list; report them by movegen index
+        const int i = (int)(ent[e].child >> kMoveIdxShift);
+        if (visits) visits[i] = (int32_t)(ent[e].n & kVisitMask);
+        if (total_score) total_score[i] = ent[e].W;
     }
     return AZ_OK;
 }
@@ -633,16 +672,15 @@ extern "C" int az_pool_pv(az_pool *pool, int game, az_move *moves, int32_t *visi
     while (n < max_len && node >= 0) {                      // select_principal_variation(best=True), engine.py:331-336
         AZ_CUDA(cudaMemcpy(slot.data(), grp.dev.nodes + ((size_t)local * grp.dev.C + node) * kNodeStride, kNodeStride, cudaMemcpyDeviceToHost));
         const NodeHdr *h = reinterpret_cast<const NodeHdr *>(slot.data());
-        const uint32_t *nv = reinterpret_cast<const uint32_t *>(slot.data() + kOffN);
-        const int32_t *ch = reinterpret_cast<const int32_t *>(slot.data() + kOffChild);
+        const Entry *ent = reinterpret_cast<const Entry *>(slot.data() + kOffEntry);
         int best = -1;
-        for (int i = 0; i < h->n_moves; ++i)
-            if (ch[i] >= 0 && (best < 0 || nv[i] > nv[best])) best = i;      // max(): first of the most visited edges
+        for (int e = 0; e < h->k; ++e)                     // max(): first of the most visited edges, in order of creation
+            if (best < 0 || (ent[e].n & kVisitMask) > (ent[best].n & kVisitMask)) best = e;   // (engine.py's dict order)
         if (best < 0) break;
-        moves[n] = reinterpret_cast<const uint16_t *>(slot.data() + kOffMove)[best];
-        if (visits) visits[n] = (int32_t)nv[best];
+        moves[n] = reinterpret_cast<const uint16_t *>(slot.data() + kOffMove)[ent[best].child >> kMoveIdxShift];
+        if (visits) visits[n] = (int32_t)(ent[best].n & kVisitMask);
         ++n;
-        node = ch[best] & kChildMask;
+        node = (int)(ent[best].child & kChildMask);
     }
     *len_out = n;
     return AZ_OK;
@@ -669,9 +707,8 @@ extern "C" int az_pool_debug_nodes(az_pool *pool, int game, uint64_t *own, uint6
         own[n] = h->own; opp[n] = h->opp; turn[n] = h->turn;
         if (visits) visits[n] = h->N;
         ++n;
-        const int32_t *ch = reinterpret_cast<const int32_t *>(nd + kOffChild);
-        for (int i = 0; i < h->n_moves; ++i)
-            if (ch[i] >= 0) queue.push_back(ch[i] & kChildMask);
+        const Entry *ent = reinterpret_cast<const Entry *>(nd + kOffEntry);
+        for (int e = 0; e < h->k; ++e) queue.push_back((int)(ent[e].child & kChildMask));
     }
     *n_out = n;
     return AZ_OK;
@@ -699,28 +736,22 @@ extern "C" int az_pool_play(az_pool *pool, int game, az_move move)
 
 namespace {
 
-// `ticks` iterations of (tree kernel, net kernel) per group, the groups' launches interleaved on their own streams,
-// then one drain of finished games.  The first tick of every call is run with the groups serialised and is timed
-// with CUDA events (tree and net kernel each alone on the GPU): that sample feeds tree_seconds / net_seconds.
+// `ticks` (<= kTicksPerDrain) iterations of (tree kernel, net kernel) per group, the groups' launches interleaved on their
+// own streams, then one drain of finished games.  Every tick is bracketed by CUDA events on the launching stream; after the
+// drain's synchronisation the per-launch times are summed into tree_seconds / net_seconds (with several groups these are
+// launch-to-completion times of overlapping kernels).
 int run_ticks(az_pool *pool, FILE *out, bool copy_records, int ticks, int64_t *games)
 {
     int rc = AZ_OK;
     const size_t ng = pool->groups.size();
     for (int t = 0; t < ticks && rc == AZ_OK; ++t) {
-        const bool timed = (t == 0);
-        if (timed && ng > 1 && (rc = sync_all(pool))) return rc;
         for (size_t gi = 0; gi < ng && rc == AZ_OK; ++gi) {
             Group &grp = pool->groups[gi];
-            const bool trace = !grp.trace.empty() && t < kTicksPerDrain;
-            if (timed) cudaEventRecord(grp.ev[0], grp.stream);
-            if (trace) cudaEventRecord(grp.trace[3 * t], grp.stream);
+            cudaEventRecord(grp.ev[3 * t], grp.stream);
             rc = launch_tree(pool, grp);
-            if (timed) cudaEventRecord(grp.ev[1], grp.stream);
-            if (trace) cudaEventRecord(grp.trace[3 * t + 1], grp.stream);
+            cudaEventRecord(grp.ev[3 * t + 1], grp.stream);
             if (rc == AZ_OK) rc = launch_net(pool, grp);
-            if (timed) cudaEventRecord(grp.ev[2], grp.stream);
-            if (trace) cudaEventRecord(grp.trace[3 * t + 2], grp.stream);
-            if (timed && ng > 1 && gi == 0) AZ_CUDA(cudaStreamSynchronize(grp.stream));   // keep the sample free of overlap
+            cudaEventRecord(grp.ev[3 * t + 2], grp.stream);
         }
         pool->ticks++;
     }
@@ -729,19 +760,14 @@ int run_ticks(az_pool *pool, FILE *out, bool copy_records, int ticks, int64_t *g
         if ((rc = drain_finished(pool, grp, out, games, copy_records))) return rc;
     if ((rc = sync_all(pool))) return rc;
     for (Group &grp : pool->groups)
-        for (int t = 1; t < ticks && !grp.trace.empty(); ++t) {
+        for (int t = 0; t < ticks; ++t) {
             float a = 0.f, b = 0.f, c = 0.f;
-            cudaEventElapsedTime(&a, grp.trace[3 * t], grp.trace[3 * t + 1]);
-            cudaEventElapsedTime(&b, grp.trace[3 * t + 1], grp.trace[3 * t + 2]);
-            cudaEventElapsedTime(&c, grp.trace[3 * t - 1], grp.trace[3 * t]);
-            grp.trace_tree_ms += a; grp.trace_net_ms += b; grp.trace_gap_ms += c; grp.trace_n++;
+            if (cudaEventElapsedTime(&a, grp.ev[3 * t], grp.ev[3 * t + 1]) != cudaSuccess ||
+                cudaEventElapsedTime(&b, grp.ev[3 * t + 1], grp.ev[3 * t + 2]) != cudaSuccess) continue;
+            pool->tree_seconds += a * 1e-3;
+            pool->net_seconds += b * 1e-3;
+            if (t > 0 && cudaEventElapsedTime(&c, grp.ev[3 * t - 1], grp.ev[3 * t]) == cudaSuccess) { grp.trace_gap_ms += c; grp.trace_n++; }
         }
-    float ms_tree = 0.f, ms_net = 0.f;
-    Group &g0 = pool->groups[0];
-    if (cudaEventElapsedTime(&ms_tree, g0.ev[0], g0.ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms_net, g0.ev[1], g0.ev[2]) == cudaSuccess) {
-        pool->tree_seconds += ms_tree * 1e-3 * ticks * ng;      // extrapolated from the sampled (group 0, un-overlapped) tick
-        pool->net_seconds += ms_net * 1e-3 * ticks * ng;
-    }
     return AZ_OK;
 }
 }  // namespace
@@ -803,13 +829,18 @@ extern "C" int az_selfplay_ticks(az_pool *pool, const char *output_path, int64_t
 
 // ---------------------------------------------------------------------------------------------
 // legacy ABI (link.py:8-32).  Process-global like the reference (self_play_client.cpp:591-602).
-// Two halves of the pool play the role of the two fill buffers: get_workload() alternates between
-// them, so while the caller evaluates buffer i the other half's answers can already be applied.
+// thread_count == 2*buffer_entries (what accelerated_generate_games.py:70-77 passes): two halves of the pool play the
+// role of the two fill buffers; get_workload() alternates between them, so while the caller evaluates buffer i the other
+// half's answers can already be applied.  buffer_entries <= thread_count < 2*buffer_entries (the reference accepts any
+// count up to 2*entries, :683-706, and needs at least `entries` workers to ever fill a buffer): ONE pool of thread_count
+// games whose first buffer_entries requests are handed out per workload, the rest stay queued -- as in the reference,
+// only one workload can then be outstanding at a time.
 // ---------------------------------------------------------------------------------------------
 namespace {
 struct Legacy {
     az_context *ctx = nullptr;
-    az_pool *half[2] = {nullptr, nullptr};
+    az_pool *half[2] = {nullptr, nullptr};       // single-pool mode: both point at the same pool
+    bool single = false;
     float *fill[2] = {nullptr, nullptr};
     int entries = 0;
     int next = 0;
@@ -830,8 +861,9 @@ extern "C" void launch_threads(char *output_path, int visits, float *fill_buffer
                                int thread_count)
 {
     if (g_legacy.ctx) legacy_die("launch_threads called twice without shutdown");
-    if (!fill_buffer1 || !fill_buffer2 || buffer_entries < 1 || thread_count != 2 * buffer_entries) {
-        az_fail(AZ_ERR_ARG, "need two fill buffers and thread_count == 2*buffer_entries (got %d, %d)", buffer_entries, thread_count);
+    if (!fill_buffer1 || !fill_buffer2 || buffer_entries < 1 || thread_count < buffer_entries || thread_count > 2 * buffer_entries) {
+        az_fail(AZ_ERR_ARG, "need two fill buffers and buffer_entries <= thread_count <= 2*buffer_entries (got %d entries, %d threads)",
+                buffer_entries, thread_count);
         legacy_die("launch_threads");
     }
     const char *dev_env = getenv("AZ_DEVICE");
@@ -846,10 +878,11 @@ extern "C" void launch_threads(char *output_path, int visits, float *fill_buffer
     g_legacy.fill[1] = fill_buffer2;
     g_legacy.entries = buffer_entries;
     g_legacy.next = 0;
+    g_legacy.single = thread_count != 2 * buffer_entries;
     g_legacy.staging.resize((size_t)buffer_entries * AZ_FEATURES);
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < (g_legacy.single ? 1 : 2); ++h) {
         az_pool_config cfg{};
-        cfg.games = buffer_entries;
+        cfg.games = g_legacy.single ? thread_count : buffer_entries;
         cfg.visits = visits;
         cfg.max_plies = 400;
         cfg.noise = 1;
@@ -858,15 +891,21 @@ extern "C" void launch_threads(char *output_path, int visits, float *fill_buffer
         cfg.steps_per_tick = 64;
         cfg.seed = g_legacy.ctx->seed + 0x9E3779B97F4A7C15ULL * (h + 1);
         if (az_pool_create(g_legacy.ctx, &cfg, &g_legacy.half[h])) legacy_die("az_pool_create");
+        g_legacy.half[h]->groups[0].dev.cap = buffer_entries;      // a workload is exactly one fill buffer
         g_legacy.waiting[h] = false;
     }
+    if (g_legacy.single) { g_legacy.half[1] = g_legacy.half[0]; g_legacy.waiting[1] = false; }
 }
 
 extern "C" int get_workload(void)
 {
     if (!g_legacy.ctx) { az_fail(AZ_ERR_STATE, "launch_threads not called"); legacy_die("get_workload"); }
     const int h = g_legacy.next;
-    if (g_legacy.waiting[h]) { az_fail(AZ_ERR_STATE, "buffer %d was handed out and not completed", h); legacy_die("get_workload"); }
+    if (g_legacy.waiting[h] || (g_legacy.single && g_legacy.waiting[h ^ 1])) {
+        az_fail(AZ_ERR_STATE, g_legacy.single ? "thread_count < 2*buffer_entries: only one workload can be outstanding (the reference would block here)"
+                                              : "buffer %d was handed out and not completed", h);
+        legacy_die("get_workload");
+    }
     az_pool *pool = g_legacy.half[h];
     // the reference hands out a buffer only when all `buffer_entries` slots are filled: every game of this
     // half must be blocked on an evaluation.  Games that end are restarted inside the tick, so this terminates.
@@ -899,7 +938,7 @@ extern "C" void shutdown(void)
 {
     if (!g_legacy.ctx) return;
     for (int h = 0; h < 2; ++h) {
-        az_pool_destroy(g_legacy.half[h]);
+        if (h == 0 || !g_legacy.single) az_pool_destroy(g_legacy.half[h]);
         g_legacy.half[h] = nullptr;
         g_legacy.waiting[h] = false;
     }
@@ -907,4 +946,40 @@ extern "C" void shutdown(void)
     g_legacy.out = nullptr;
     az_destroy(g_legacy.ctx);
     g_legacy.ctx = nullptr;                    // cleared so launch_threads may be called again (:744-748)
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistical test hooks (not in the public header; tests/test_rng_gpu.py): run the tick kernel's own Gamma sampler and
+// its visit-proportional move sampler n times with independent counter-based streams.  Host pointers in and out.
+// ---------------------------------------------------------------------------------------------
+extern "C" int az_debug_gamma(az_context *ctx, double alpha, uint64_t seed, int n, double *out)
+{
+    AZ_REQUIRE(ctx && out && n > 0 && alpha > 0.0 && alpha < 1.0, AZ_ERR_ARG, "az_debug_gamma: bad argument");
+    AZ_REQUIRE(ctx->scratch[0].reserve(sizeof(double) * (size_t)n) == 0, AZ_ERR_CUDA, "scratch alloc");
+    aztree_launch_debug_gamma(alpha, seed, n, ctx->scratch[0].as<double>(), ctx->stream);
+    ctx->launches++;
+    AZ_CUDA(cudaMemcpyAsync(out, ctx->scratch[0].ptr, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    AZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+extern "C" int az_debug_sample_moves(az_context *ctx, const int32_t *visits, int n_moves, uint64_t seed, int n, int32_t *out)
+{
+    AZ_REQUIRE(ctx && visits && out && n > 0 && n_moves > 0 && n_moves < AZ_MAX_MOVES, AZ_ERR_ARG, "az_debug_sample_moves: bad argument");
+    int64_t total = 0;
+    for (int i = 0; i < n_moves; ++i) {
+        AZ_REQUIRE(visits[i] >= 0, AZ_ERR_ARG, "az_debug_sample_moves: negative visit count");
+        total += visits[i];
+    }
+    AZ_REQUIRE(total > 0 && total < (1 << 30), AZ_ERR_ARG, "az_debug_sample_moves: visit counts must sum to 1..2^30");
+    AZ_REQUIRE(ctx->scratch[0].reserve(sizeof(int32_t) * (size_t)n_moves) == 0 && ctx->scratch[1].reserve(sizeof(int32_t) * (size_t)n) == 0,
+               AZ_ERR_CUDA, "scratch alloc");
+    AZ_CUDA(cudaMemcpyAsync(ctx->scratch[0].ptr, visits, sizeof(int32_t) * (size_t)n_moves, cudaMemcpyHostToDevice, ctx->stream));
+    aztree_launch_debug_sample(ctx->scratch[0].as<int32_t>(), n_moves, (int)total, seed, n, ctx->scratch[1].as<int32_t>(), ctx->stream);
+    ctx->launches++;
+    AZ_CUDA(cudaMemcpyAsync(out, ctx->scratch[1].ptr, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    AZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
 }

@@ -1,21 +1,32 @@
 // az_tree.cuh -- device-resident PUCT trees: memory layout shared by az_tree.cu (kernels)
 // and az_pool.cu (host runtime).  Internal.
 //
-// One tree per game, one fixed-stride slot per node (no allocator metadata on the hot path):
+// One tree per game, one fixed-stride slot per node (no allocator metadata on the hot path).
 //
-//   node slot (9216 B, 128-B aligned):
-//     [   0,   64)  header: position, value, child count L, visit count N, flags
-//     [  64, 2112)  P[256]      f64  prior                      (self_play_client.cpp:151 posterior)
-//     [2112, 4160)  W[256]      f64  edge_total_score           (:283)
-//     [4160, 6208)  Q[256]      f64  W/n, refreshed by backup   (:288-292 get_edge_score; select never divides W)
-//     [6208, 7232)  n[256]      u32  edge_visits                (:282; integral, so exact as u32)
-//     [7232, 8256)  child[256]  i32  child node index, -1 = no edge yet (:281)
+// The reference's select_action (self_play_client.cpp:333-366) scores every legal move of a node on every visit.
+// A move WITHOUT an edge scores fl(sqrt(1+N) * P) + 0 (:313-315,322), which is monotone in P, so among those moves only
+// the one with the largest prior can win (exactly equal priors: the one that comes last in the reference's
+// unordered_map iteration order).  A node therefore keeps
+//   * a dense list of the moves that HAVE an edge, in order of creation ("entries": prior, total score, visits,
+//     child), and
+//   * one CANDIDATE among the others (its movegen index and prior) plus the next smaller prior value -- the latter
+//     only to detect the rare case of two different priors rounding to the same product, which a full scan resolves.
+// A descent touches the header and the k entries of a node, not its L moves: for the deep nodes of a tree (k of a
+// handful, L around 50) that is one or two 128-byte lines instead of ~20, and the hot part of all trees fits the L2.
+// oracle/tree_model.c restates this algorithm on the CPU and tests/test_tree_model.py checks it against the
+// reference-order search (exact ties, re-rooting, adversarial priors).
+//
+//   node slot (kNodeStride bytes, 128-B aligned):
+//     [   0,   64)  NodeHdr
+//     [  64, 6184)  Entry[255]  24 B each: P f64, W f64 (edge_total_score :283), n u32 (edge_visits :282, bits 0..22;
+//                               bits 23..31: how many entries the CHILD had when this edge was last extended below --
+//                               a load hint), child u32 (node index bits 0..23, movegen index of the move bits 24..31)
+//     [6208, 8256)  P[256]      f64  prior of every move in movegen order (:151 posterior)
 //     [8256, 8768)  move[256]   u16  from | to<<8, reference movegen order (cpp/movegen.cpp:16-66)
-//     [8768, 9024)  rank[256]   u8   position of the move in the reference's hash-map iteration order
-//                                    (select_action's `>=` tie-break walks that order, :345-358); filled in
-//                                    lazily, the first time a node actually sees an exact tie at its maximum
-//   Children of a node are a struct-of-arrays inside its slot, so a warp reads P/W/n of 32 children
-//   with three coalesced loads.  L < 256 is the reference's own bound (movegen.cpp:69).
+//     [8768, 9024)  rank[256]   u8   position of the move in the reference's hash-map iteration order (select_action's
+//                                    `>=` tie-break walks that order, :345-358); filled in lazily, the first time a
+//                                    node actually sees an exact tie
+//     [9024, 9056)  visited     256-bit set: move i has an edge
 //
 // Dead subtrees are recycled lazily: re-rooting pushes the discarded siblings on a per-game stack;
 // allocating a node pops one entry and pushes that node's children.  The pool therefore never holds
@@ -25,13 +36,15 @@
 
 namespace aztree {
 
-constexpr int kNodeStride = 9216;
-constexpr int kOffP = 64, kOffW = 2112, kOffQ = 4160, kOffN = 6208, kOffChild = 7232, kOffMove = 8256, kOffRank = 8768;
+constexpr int kNodeStride = 9088;
+constexpr int kOffEntry = 64, kEntryBytes = 24, kMaxEntries = 255;
+constexpr int kOffP = 6208, kOffMove = 8256, kOffRank = 8768, kOffVisited = 9024;
 constexpr int kMaxPath = 1024;
-// child[] entries: bits 0..23 node index, bits 24..27 ceil(L_child / 32) -- how many 32-child groups a descent must
-// load for that child, so a level fetches the child's real fan-out instead of a fixed 128 entries; -1 = no edge yet
-constexpr int32_t kChildMask = 0x00ffffff;
-constexpr int kChildGroupShift = 24;
+constexpr uint32_t kVisitMask = 0x007fffffu;     // Entry::n: visit count (pool visits are capped at 2^22)
+constexpr int kHintShift = 23;
+constexpr uint32_t kChildMask = 0x00ffffffu;     // Entry::child: node index
+constexpr int kMoveIdxShift = 24;
+constexpr int kNoCand = 0xff;
 constexpr int kRecWordsPerPly = 6 + 2 * 256;    // worst-case record words per ply
 
 enum : uint32_t {
@@ -46,14 +59,24 @@ enum : int32_t { ERR_NODES = 1, ERR_PATH = 2, ERR_MOVES = 3 };
 struct __align__(16) NodeHdr {
     uint64_t own, opp;       // pieces of the side to move / of the opponent
     double value;            // evals.value: from the side to move's point of view
-    int32_t n_moves;         // L; 0 for adjudicated (terminal) nodes
+    double cand_p;           // prior of the candidate (0 when there is none)
+    double cand2_p;          // largest prior below cand_p among the moves without an edge; < 0: none
     int32_t N;               // all_edge_visits
-    int32_t turn;            // absolute side to move: 0 = x, 1 = o
-    uint32_t flags;
-    int32_t reserved;
-    int32_t pad[5];
+    uint16_t n_moves;        // L; 0 for adjudicated (terminal) nodes
+    uint8_t k;               // moves with an edge = entries in use
+    uint8_t cand;            // movegen index of the candidate, kNoCand: every move has an edge
+    uint8_t turn;            // absolute side to move: 0 = x, 1 = o
+    uint8_t flags;
+    uint16_t pad0;
+    uint32_t pad[3];
 };
 static_assert(sizeof(NodeHdr) == 64, "node header is 64 bytes");
+
+struct Entry {
+    double P, W;
+    uint32_t n, child;
+};
+static_assert(sizeof(Entry) == kEntryBytes, "entry is 24 bytes");
 
 struct __align__(16) Game {
     int32_t status;
@@ -85,7 +108,7 @@ struct DoneEntry {
 struct PoolDev {
     uint8_t *nodes;          // [G][C][kNodeStride]
     Game *games;             // [G]
-    uint32_t *path;          // [G][kMaxPath]  node << 8 | slot
+    uint32_t *path;          // [G][kMaxPath]  node << 8 | entry
     uint32_t *gstack;        // [G][C]
     az_position *req_pos;    // [G]
     int32_t *req_game;       // [G]
@@ -99,13 +122,14 @@ struct PoolDev {
     int32_t *done_count;     // [1]
     int32_t G, C, visits, max_plies, noise, auto_play, steps_per_tick;
     int32_t levels_per_tick; // bound on tree levels a game may descend per tick (tail latency of deep endgame lines)
+    int32_t tick_cycles;     // > 0: a game also stops starting new tree levels this many SM clock cycles into the tick
     int32_t cap;             // evaluations served per tick: a whole number of net-kernel rounds; later requests are re-queued
     int32_t consume;         // 1: evaluations of the previous requests are in logits/values; 0: top-up tick, leave waiting games alone
     int32_t tick_slot;       // slot of req_count this tick appends its requests to
     int32_t game_base;       // global index of this group's game 0 (RNG streams are keyed by the global game index)
     uint32_t rec_cap_words;
     uint64_t seed;
-    int32_t full_fetch;      // experiment (AZ_TREE_FULL_FETCH=1): always load 128 children per level, ignoring the edge's group count
+    int32_t force_slow;      // test knob (AZ_TREE_FORCE_SLOW=1): resolve every candidate by the full scan
     unsigned long long *prof;   // AZ_POOL_PROFILE=1: [G][8] clock cycles per phase of the last tick (debug aid, normally nullptr)
 };
 

@@ -43,6 +43,7 @@ _native.register("az_pool_set_visits", C.c_int, [_vp, C.c_int])
 _native.register("az_pool_run", C.c_int, [_vp, C.c_int, C.POINTER(C.c_int32)])
 _native.register("az_pool_collect", C.c_int, [_vp, _vp, C.POINTER(C.c_int32)])
 _native.register("az_pool_provide", C.c_int, [_vp, _vp, _vp])
+_native.register("az_pool_provide_n", C.c_int, [_vp, _vp, _vp, C.c_int32])
 _native.register("az_pool_root", C.c_int, [_vp, C.c_int, C.POINTER(Position), C.POINTER(C.c_int32), _vp, _vp, _vp, _vp,
                                            C.POINTER(C.c_int32), C.POINTER(C.c_double)])
 _native.register("az_pool_play", C.c_int, [_vp, C.c_int, C.c_uint16])
@@ -119,7 +120,9 @@ class Pool:
         values = np.ascontiguousarray(values, dtype=np.float32).reshape(-1)
         if len(values) != len(logits):
             raise AzError(-1, "provide: %d logit rows but %d values" % (len(logits), len(values)))
-        check(lib().az_pool_provide(self._h, C.c_void_p(logits.ctypes.data), C.c_void_p(values.ctypes.data)))
+        # the library copies one row per outstanding request: it is told how many rows these arrays really hold and
+        # refuses a mismatch instead of reading past their end
+        check(lib().az_pool_provide_n(self._h, C.c_void_p(logits.ctypes.data), C.c_void_p(values.ctypes.data), len(logits)))
 
     def run_external(self, evaluator):
         """Drive the pool with ``evaluator(features[n,7,7,4]) -> (logits[n,833], values[n])`` until idle."""

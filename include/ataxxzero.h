@@ -181,6 +181,8 @@ int az_pool_run(az_pool *pool, int max_ticks, int32_t *idle_out);
 int az_pool_collect(az_pool *pool, float *features, int32_t *n_requests);
 /* ... and hand back logits [n][833] / values [n] in the same order (complete_workload semantics). */
 int az_pool_provide(az_pool *pool, const float *logits, const float *values);
+/* the same with the row count of the caller's arrays stated: AZ_ERR_ARG unless n_rows == the n of az_pool_collect */
+int az_pool_provide_n(az_pool *pool, const float *logits, const float *values, int32_t n_rows);
 /* root statistics in reference movegen order (visits[i] = edge_visits or 0 when no edge exists) */
 int az_pool_root(az_pool *pool, int game, az_position *pos, int32_t *n_moves, az_move *moves, int32_t *visits,
                  double *total_score, double *prior, int32_t *root_visits, double *root_value);
@@ -218,7 +220,9 @@ int az_samples_extract_dev(az_context *ctx, const void *d_plies, const void *d_o
 /* ---------------- legacy 4-function ABI (link.py:8-32; self_play_client.cpp:683,708,723,740) -------- */
 /* Same names, arguments and blocking behaviour.  The trees live on GPU 0 (or $AZ_DEVICE); the caller is
  * the evaluator: get_workload() fills fill_buffer{1,2} with `buffer_entries` feature planes and returns the
- * buffer index, complete_workload() takes the matching logits/values.  thread_count must be 2*buffer_entries. */
+ * buffer index, complete_workload() takes the matching logits/values.  buffer_entries <= thread_count <= 2*buffer_entries
+ * (self_play_client.cpp:683-706 accepts any count up to 2*entries and needs `entries` workers to ever fill a buffer); with
+ * fewer than 2*buffer_entries threads only one workload can be outstanding at a time, as in the reference. */
 void launch_threads(char *output_path, int visits, float *fill_buffer1, float *fill_buffer2, int buffer_entries,
                     int thread_count);
 int get_workload(void);

@@ -434,6 +434,28 @@ int ao_umap_order(const int32_t *from, const int32_t *to, int n, int start_bucke
 /* MCTS                                                               */
 /* ------------------------------------------------------------------ */
 
+/* Test hook (NULL in normal use): perturbs the priors of every freshly populated node, in this oracle and in the
+ * device-algorithm model (tree_model.c) alike, to provoke the tie situations real evaluators almost never produce. */
+void (*ao_prior_hook)(double *prior, int n) = NULL;
+
+static void perturb_quantise(double *p, int n)       /* many exactly equal priors among unequal logits */
+{
+    for (int i = 0; i < n; i++) p[i] = floor(p[i] * 64.0 + 0.5) / 64.0 + 1.0 / 1024.0;
+}
+static void perturb_adjacent(double *p, int n)       /* pairs of ADJACENT doubles: different priors, often equal products */
+{
+    for (int i = 0; i + 1 < n; i += 2) p[i + 1] = nextafter(p[i], 0.0);
+}
+static void perturb_adjacent_groups(double *p, int n) /* runs of 4 consecutive doubles sharing one leading value */
+{
+    for (int i = 0; i < n; i++)
+        if (i % 4) p[i] = nextafter(p[i - 1], 0.0);
+}
+void ao_set_prior_perturbation(int mode)
+{
+    ao_prior_hook = mode == 1 ? perturb_quantise : mode == 2 ? perturb_adjacent : mode == 3 ? perturb_adjacent_groups : NULL;
+}
+
 typedef struct ao_node {
     ao_position board;
     int populated, game_over;
@@ -489,6 +511,7 @@ static void node_populate(ao_mcts *m, ao_node *n)
     m->evals++;
     n->value = (double)v;
     ao_priors(logits, n->from, n->to, n->n_moves, n->prior);
+    if (ao_prior_hook) ao_prior_hook(n->prior, n->n_moves);
     n->map_buckets = ao_umap_order(n->from, n->to, n->n_moves, n->map_buckets, n->order);
     n->populated = 1;
 }

@@ -92,6 +92,12 @@ void ao_probe_eval_batch(const float *feats, int n, float *logits, float *values
 /* Degenerate evaluator: all logits 0, value 0 -> every prior ties (exercises map order). */
 void ao_uniform_eval(void *ctx, const float feats[AO_FEATURES], float logits[AO_LOGITS], float *value);
 
+/* test hook: 0 none, 1 heavy quantisation (exact ties), 2 adjacent-double pairs, 3 runs of 4 adjacent doubles */
+void ao_set_prior_perturbation(int mode);
+
+/* ---- tree_model.c: CPU model of the device tree algorithm (candidate + visited list), checked against ao_mcts ---- */
+long tm_selftest(const char *fen, int visits, int evaluator, int plays, int force_slow, long *counters_out);
+
 /* convenience: search `visits` from fen with a named evaluator (0 probe, 1 uniform),
  * fill root distribution; returns n_moves or <0 on error. */
 int ao_search_fen(const char *fen, int visits, int evaluator, int32_t *from, int32_t *to,

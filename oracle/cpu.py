@@ -45,8 +45,8 @@ _f32p = C.POINTER(C.c_float)
 
 def build(force=False):
     """(Re)build the checker libraries with oracle/Makefile."""
-    if force or not os.path.exists(ORACLE_SO) or \
-            os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(HERE, "ataxx_oracle.c")):
+    sources = [os.path.join(HERE, f) for f in ("ataxx_oracle.c", "tree_model.c", "ataxx_oracle.h")]
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(f) for f in sources):
         subprocess.check_call(["make", "-s", "-C", HERE, "libataxx_oracle.so"])
     if os.path.isdir("/root/reference/cpp") and (force or not os.path.exists(REF_SO)):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])

@@ -1,0 +1,206 @@
+"""Statistical parity of the two random rows of the path (a11 Dirichlet root noise,
+self_play_client.cpp:250-271; a18 move sampling proportional to visits, :495-506) plus the host-visible
+consequences of the compact node layout (forced full-scan selection, legacy thread counts, row-count checks).
+
+The reference draws from a racy global std::mt19937; its streams cannot be reproduced, so the check is on the
+DISTRIBUTIONS its code defines: g_k ~ Gamma(0.15, 1), noise = g / sum(g) ~ Dirichlet(0.15), P <- 0.25 noise + 0.75 P,
+and P(move i) = n_i / N."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ALPHA, WEIGHT = 0.15, 0.25     # self_play_client.cpp:36-37
+
+
+def _lib():
+    from ataxxzero_b200 import _native
+    lib = _native.lib()
+    lib.az_debug_gamma.restype = C.c_int
+    lib.az_debug_gamma.argtypes = [C.c_void_p, C.c_double, C.c_uint64, C.c_int, C.c_void_p]
+    lib.az_debug_sample_moves.restype = C.c_int
+    lib.az_debug_sample_moves.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_void_p]
+    return lib
+
+
+def test_gamma_sampler_distribution(ctx):
+    """std::gamma_distribution<double>(0.15, 1.0) (:252): mean = variance = 0.15, and the whole CDF (KS test)."""
+    from scipy import stats
+    from ataxxzero_b200 import _native
+    n = 200000
+    out = np.zeros(n, dtype=np.float64)
+    _native.check(_lib().az_debug_gamma(ctx.handle, ALPHA, 12345, n, C.c_void_p(out.ctypes.data)))
+    assert (out > 0).all() and np.isfinite(out).all()
+    se_mean = (ALPHA / n) ** 0.5
+    assert abs(out.mean() - ALPHA) < 4 * se_mean, (out.mean(), se_mean)
+    # Var of the sample variance of Gamma(a): (mu4 - sigma^4)/n with mu4 = 3a^2 + 6a
+    se_var = ((3 * ALPHA ** 2 + 6 * ALPHA - ALPHA ** 2) / n) ** 0.5
+    assert abs(out.var() - ALPHA) < 4 * se_var, (out.var(), se_var)
+    ks = stats.kstest(out, "gamma", args=(ALPHA,))
+    assert ks.pvalue > 1e-4, ks
+    # a different seed gives a different stream, the same seed the same one
+    again, other = np.zeros(1000), np.zeros(1000)
+    _native.check(_lib().az_debug_gamma(ctx.handle, ALPHA, 12345, 1000, C.c_void_p(again.ctypes.data)))
+    _native.check(_lib().az_debug_gamma(ctx.handle, ALPHA, 54321, 1000, C.c_void_p(other.ctypes.data)))
+    assert (again == out[:1000]).all() and (other != out[:1000]).any()
+
+
+def test_dirichlet_root_noise_marginals(ctx, oracle):
+    """20 000 fresh roots of the opening position, uniform evaluation: (P_noisy - 0.75 P) / 0.25 must be a
+    Dirichlet(0.15 x 16) draw -- components sum to 1, each marginal is Beta(0.15, 2.25) (mean 1/16, known
+    variance, KS test), different games get different draws."""
+    from scipy import stats
+    from ataxxzero_b200 import search
+    games = 20000
+    with search.Pool(ctx, games, 1, eval_mode=search.EVAL_EXTERNAL, noise=True, auto_play=False, node_capacity=6, seed=99) as pool:
+        feats = pool.collect()
+        assert len(feats) == games
+        pool.provide(np.zeros((games, 833), dtype=np.float32), np.zeros(games, dtype=np.float32))
+        pool.collect()                                    # consumes the evaluations: priors + noise are in the roots now
+        roots = [pool.root(g) for g in range(0, games, 1)]
+    L = len(roots[0]["moves"])
+    assert L == 16
+    noisy = np.array([r["prior"] for r in roots])
+    clean = 1.0 / L                                        # uniform logits: every legal move has prior 1/16
+    d = (noisy - (1 - WEIGHT) * clean) / WEIGHT
+    assert np.abs(d.sum(axis=1) - 1.0).max() < 1e-9
+    assert d.min() > -1e-12
+    a0 = ALPHA * L
+    var = ALPHA * (a0 - ALPHA) / (a0 * a0 * (a0 + 1))
+    se = (var / games) ** 0.5
+    for k in range(L):
+        col = np.clip(d[:, k], 0, 1)
+        assert abs(col.mean() - 1.0 / L) < 4.5 * se, (k, col.mean(), se)
+        assert abs(col.var() - var) < 0.12 * var, (k, col.var(), var)
+        ks = stats.kstest(col, "beta", args=(ALPHA, a0 - ALPHA))
+        assert ks.pvalue > 1e-5, (k, ks)
+    assert len({tuple(np.round(row, 12)) for row in d[:500]}) == 500       # independent streams per game
+
+
+def test_move_sampling_proportional_to_visits(ctx):
+    """fixed root visit table, 50 000 independent draws of the kernel's sampler: chi-square against n_i / N; moves
+    without an edge are never played"""
+    from scipy import stats
+    from ataxxzero_b200 import _native
+    visits = np.array([0, 5, 0, 120, 3, 472, 0, 1, 60, 0, 0, 139, 1, 0], dtype=np.int32)
+    n = 50000
+    out = np.zeros(n, dtype=np.int32)
+    _native.check(_lib().az_debug_sample_moves(ctx.handle, C.c_void_p(visits.ctypes.data), len(visits), 777, n, C.c_void_p(out.ctypes.data)))
+    counts = np.bincount(out, minlength=len(visits))
+    assert counts[visits == 0].sum() == 0
+    live = visits > 0
+    expected = visits[live] / visits.sum() * n
+    chi = stats.chisquare(counts[live], expected)
+    assert chi.pvalue > 1e-4, (chi, counts, expected)
+    # single-edge table: always that edge
+    one = np.array([0, 0, 800, 0], dtype=np.int32)
+    _native.check(_lib().az_debug_sample_moves(ctx.handle, C.c_void_p(one.ctypes.data), 4, 1, 1000, C.c_void_p(out.ctypes.data)))
+    assert (out[:1000] == 2).all()
+
+
+def test_selfplay_first_moves_follow_visit_table(ctx):
+    """end to end through generate_game: with noise off every game of a pool searches the opening identically, so the
+    first moves of many games are draws from ONE visit distribution (the one a single search tree reports)"""
+    from scipy import stats
+    from ataxxzero_b200 import model, net, rules, search
+    net.load_weights(ctx, model.Network.random_init(seed=0))
+    games, visits = 2048, 60
+    os.environ["AZ_REQ_CAP"] = "0"          # serve every request every tick: the games stay in lockstep up to their first move
+    try:
+        pool = search.Pool(ctx, games, visits, eval_mode=search.EVAL_BF16, noise=False, auto_play=True, seed=6)
+    finally:
+        del os.environ["AZ_REQ_CAP"]
+    with pool:
+        for _ in range(4 * visits):
+            pool.selfplay_ticks(1)
+            if pool.root(0)["position"].ply >= 1:
+                break
+        after_first = [pool.root(g)["position"] for g in range(games)]
+    assert all(p.ply == 1 for p in after_first)
+    with search.Pool(ctx, 1, visits, eval_mode=search.EVAL_BF16, noise=False, auto_play=False) as tree:
+        tree.run()
+        root = tree.root(0)
+    weights = np.array(root["visits"], dtype=np.float64)
+    assert weights.sum() == root["root_visits"] >= visits
+    start = rules.set_board(rules.START_FEN)
+    after = rules.makemove_batch(ctx, rules.positions_array([start] * len(root["moves"])), root["moves"])
+    index = {(int(a["pieces"][0]), int(a["pieces"][1])): i for i, a in enumerate(after)}
+    assert len(index) == len(root["moves"])               # distinct moves lead to distinct positions at the opening
+    counts = np.zeros(len(root["moves"]))
+    for p in after_first:
+        counts[index[(p.pieces[0], p.pieces[1])]] += 1
+    live = weights > 0
+    assert counts[~live].sum() == 0
+    chi = stats.chisquare(counts[live], weights[live] / weights.sum() * games)
+    assert chi.pvalue > 1e-4, (chi, counts, weights)
+    assert len(set(counts[live])) > 1 or live.sum() == 1
+
+
+def test_forced_full_scan_selection_matches_goldens(ctx, oracle):
+    """AZ_TREE_FORCE_SLOW=1 resolves every candidate by the full scan over all moves without an edge (the path taken when
+    two different priors round to the same product): visit counts and total scores must not change."""
+    from ataxxzero_b200 import rules, search
+    from oracle.cpu import START_FEN
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mcts_golden.json")))
+    fens = [START_FEN, golden.get("midgame_fen", START_FEN)]
+    os.environ["AZ_TREE_FORCE_SLOW"] = "1"
+    try:
+        for fen in fens:
+            uniform = lambda f: (np.zeros((len(f), 833), dtype=np.float32), np.zeros(len(f), dtype=np.float32))
+            for name, evalfn in (("probe", oracle.probe_eval), ("uniform", uniform)):
+                with search.Pool(ctx, 1, 600, eval_mode=search.EVAL_EXTERNAL) as pool:
+                    pool.set_root(0, rules.set_board(fen))
+                    pool.run_external(evalfn)
+                    got = pool.root(0)
+                tree = oracle.tree(oracle.set_board(fen), name)
+                tree.search(600)
+                want = tree.dist()
+                tree.close()
+                assert got["visits"] == [w[1] for w in want], (fen, name)
+                assert [float(x).hex() for x in got["total_score"]] == [float(w[2]).hex() for w in want], (fen, name)
+    finally:
+        del os.environ["AZ_TREE_FORCE_SLOW"]
+
+
+def test_provide_rejects_wrong_row_count(ctx):
+    from ataxxzero_b200 import AzError, search
+    with search.Pool(ctx, 8, 10, eval_mode=search.EVAL_EXTERNAL) as pool:
+        feats = pool.collect()
+        assert len(feats) == 8
+        with pytest.raises(AzError):
+            pool.provide(np.zeros((5, 833), dtype=np.float32), np.zeros(5, dtype=np.float32))
+        pool.provide(np.zeros((8, 833), dtype=np.float32), np.zeros(8, dtype=np.float32))   # still answerable afterwards
+
+
+def test_legacy_abi_accepts_fewer_threads(tmp_path, ctx, oracle):
+    """self_play_client.cpp:683-706 takes any thread_count <= 2*buffer_entries; with buffer_entries <= threads < 2x only one
+    workload is outstanding at a time and every workload is a full buffer"""
+    import ctypes
+    from ataxxzero_b200 import link, model, net
+    from test_selfplay_gpu import replay_and_check
+    net.load_weights(ctx, model.Network.random_init(seed=0))
+    out = str(tmp_path / "legacy_few.json")
+    entries, threads = 16, 23
+    bufs = [np.zeros((entries, 7, 7, 4), dtype=np.float32) for _ in (0, 1)]
+    link.launch_threads(out.encode(), 16, ctypes.c_void_p(bufs[0].ctypes.data), ctypes.c_void_p(bufs[1].ctypes.data), entries, threads)
+    try:
+        seen = []
+        for _ in range(8000):
+            i = link.get_workload()
+            seen.append(i)
+            assert bufs[i][..., 0].min() == 1.0
+            p, v = net.forward(ctx, bufs[i], net.BF16)
+            link.complete_workload(i, ctypes.c_void_p(p.ctypes.data), ctypes.c_void_p(v.ctypes.data))
+            if os.path.exists(out) and open(out).read().count("\n") >= 3:
+                break
+        assert seen[:4] == [0, 1, 0, 1]
+    finally:
+        link.shutdown()
+    lines = open(out).read().splitlines()
+    assert len(lines) >= 3
+    for ln in lines:
+        replay_and_check(oracle, ln, 16)
