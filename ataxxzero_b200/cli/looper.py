@@ -40,6 +40,8 @@ def generate_games(args, model_number):
     if count_games(paths) >= args.game_count:
         print("Enough games to start with!")
         return
+    if args.processes > max(args.gpus, 1):
+        print("WARNING: %d generator processes share %d GPU(s); each allocates its own node pool." % (args.processes, max(args.gpus, 1)))
     procs = [subprocess.Popen([sys.executable, "-m", "ataxxzero_b200.cli.accelerated_generate_games",
                                "--network", index_to_model_path(args, model_number), "--output-games", path,
                                "--visits", str(args.visits), "--buffer-size", str(args.buffer_size),
@@ -54,8 +56,13 @@ def generate_games(args, model_number):
     while True:
         n = count_games(paths)
         print("Game count:", n)
-        if n >= args.game_count or all(p.poll() is not None for p in procs):
+        if n >= args.game_count:
             break
+        if all(p.poll() is not None for p in procs):
+            # every generator died (bad model file, out of memory, ...) before the target was reached: the reference would
+            # block here for ever; training on too few games would be worse, so stop with the children's exit codes
+            atexit.unregister(reap)
+            raise SystemExit("generators exited with codes %r after %d of %d games" % ([p.returncode for p in procs], n, args.game_count))
         time.sleep(args.poll_seconds)
     for proc in procs:
         if proc.poll() is None:

@@ -64,7 +64,9 @@ def load_into(net, network):
 
 
 def export(net):
-    """torch modules -> model.Network: conv / FC weights + batch-norm moving statistics (gamma / beta are not saved)."""
+    """torch modules -> model.Network: conv / FC weights + batch-norm moving statistics (gamma / beta are not saved).
+    torch accumulates the UNBIASED batch variance in running_var where TF's moving_variance takes the biased one; with
+    minibatch * 49 >= 25 000 samples per channel the factor n / (n - 1) is below 1.00005 and is exported as is."""
     convs = list(net.convs) + [net.policy, net.value]
     conv = [m.weight.detach().cpu().numpy().transpose(2, 3, 1, 0).copy() for m in convs]
     conv += [net.fc_w.detach().cpu().numpy().copy(), net.fc_b.detach().cpu().numpy().copy()]
@@ -154,6 +156,10 @@ def main(argv=None):
     from .. import train_data
     args = build_parser().parse_args(argv)
     print("Arguments:", args)
+    if args.filters != azmodel.Network.FILTERS and not args.old_path:
+        # az_net_load only accepts the reference's width (model.py:16): a network of another width could be trained and
+        # exported here but not played by the self-play library, and the loop would fail one round later
+        raise SystemExit("--filters %d: libataxxzero.so is built for %d filters" % (args.filters, azmodel.Network.FILTERS))
     random.seed(123456789)                                   # train.py:103: shuffle the loaded games deterministically
     entries = train_data.load_entries(args.games, shuffle=True, rng=random)
     print("Found %i games with %i plies." % (len(entries), sum(len(e["moves"]) for e in entries)))

@@ -247,16 +247,19 @@ extern "C" int az_net_load(az_context *ctx, const float *packed, size_t count, i
 }
 
 static int net_forward_dev(az_context *ctx, const void *d_in, int in_kind, int n, int mode, void *d_logits, void *d_values,
-                           const int *d_count = nullptr, cudaStream_t stream = nullptr, int tiles = 0)
+                           const int *d_count = nullptr, cudaStream_t stream = nullptr, int tiles = 0, double *d_exps = nullptr,
+                           double *d_totals = nullptr, const int *d_out_map = nullptr)
 {
     if (!stream && ctx) stream = ctx->stream;
-    AZ_REQUIRE(ctx && (n == 0 || (d_in && d_logits && d_values)), AZ_ERR_ARG, "az_net_forward: null argument");
+    AZ_REQUIRE(ctx && (n == 0 || (d_in && (d_logits || d_exps) && d_values)), AZ_ERR_ARG, "az_net_forward: null argument");
     AZ_REQUIRE(ctx->net, AZ_ERR_STATE, "az_net_forward: no weights loaded (call az_net_load first)");
     AZ_REQUIRE(n >= 0, AZ_ERR_ARG, "az_net_forward: n=%d", n);
-    AZ_REQUIRE(mode == AZ_NET_FP32 || mode == AZ_NET_BF16, AZ_ERR_ARG, "az_net_forward: unknown mode %d", mode);
+    AZ_REQUIRE(mode == AZ_NET_FP32 || mode == AZ_NET_BF16 || mode == AZ_NET_F16, AZ_ERR_ARG, "az_net_forward: unknown mode %d", mode);
     if (n == 0) return AZ_OK;
-    if (mode == AZ_NET_BF16)
-        return az_net_tc_forward(ctx, ctx->net, d_in, in_kind, n, static_cast<float *>(d_logits), static_cast<float *>(d_values), d_count, stream, tiles);
+    if (mode == AZ_NET_BF16 || mode == AZ_NET_F16)
+        return az_net_tc_forward(ctx, ctx->net, d_in, in_kind, n, static_cast<float *>(d_logits), static_cast<float *>(d_values), d_count, stream, tiles,
+                                 d_exps, d_totals, mode == AZ_NET_F16, d_out_map);
+    AZ_REQUIRE(!d_exps && !d_out_map, AZ_ERR_ARG, "az_net_forward: softmax numerators are produced by the tensor-core kernel only");
     const int grid = (n + NB - 1) / NB;
     if (in_kind == AZ_IN_F32)
         k_net_fp32<AZ_IN_F32><<<grid, THREADS, SMEM_FP32, stream>>>(d_in, n, d_count, *ctx->net, static_cast<float *>(d_logits),
@@ -270,9 +273,9 @@ static int net_forward_dev(az_context *ctx, const void *d_in, int in_kind, int n
 }
 
 int az_net_forward_internal(az_context *ctx, const void *d_in, int in_kind, int n, int mode, float *d_logits, float *d_values,
-                            const int *d_count, cudaStream_t stream, int tiles)
+                            const int *d_count, cudaStream_t stream, int tiles, double *d_exps, double *d_totals, const int *d_out_map)
 {
-    return net_forward_dev(ctx, d_in, in_kind, n, mode, d_logits, d_values, d_count, stream, tiles);
+    return net_forward_dev(ctx, d_in, in_kind, n, mode, d_logits, d_values, d_count, stream, tiles, d_exps, d_totals, d_out_map);
 }
 
 extern "C" int az_net_forward_dev(az_context *ctx, const void *d_features, int n, int mode, void *d_logits, void *d_values)
@@ -360,6 +363,17 @@ extern "C" int az_net_forward_sym8(az_context *ctx, const float *features, int n
                AZ_ERR_CUDA, "az_net_forward_sym8: device scratch alloc");
     cudaStream_t s = ctx->stream;
     AZ_CUDA(cudaMemcpyAsync(b[0].ptr, features, fb, cudaMemcpyHostToDevice, s));
+    if (mode == AZ_NET_BF16 || mode == AZ_NET_F16) {
+        // fused: the tensor-core kernel generates the 8 images while it stages its input and averages in its head epilogue
+        int rc = az_net_tc_forward_sym8(ctx, ctx->net, b[0].ptr, AZ_IN_F32, n, b[4].as<float>(), b[5].as<float>(), mode == AZ_NET_F16);
+        if (rc) return rc;
+        AZ_CUDA(cudaMemcpyAsync(logits, b[4].ptr, lb, cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaMemcpyAsync(values, b[5].ptr, 4 * nn, cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaStreamSynchronize(s));
+        AZ_CUDA(cudaGetLastError());
+        return AZ_OK;
+    }
+    AZ_REQUIRE(mode == AZ_NET_FP32, AZ_ERR_ARG, "az_net_forward_sym8: unknown mode %d", mode);
     k_sym8_expand<<<(n * 8 * 49 + 255) / 256, 256, 0, s>>>(b[0].as<float4>(), n, b[1].as<float4>());
     int rc = net_forward_dev(ctx, b[1].ptr, AZ_IN_F32, 8 * n, mode, b[2].ptr, b[3].ptr);
     if (rc) return rc;

@@ -2,6 +2,7 @@
 #pragma once
 #include "az_common.h"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 constexpr int AZ_F = 128;            // filters (model.py:16)
 constexpr float AZ_BN_EPS = 1e-3f;
@@ -28,6 +29,7 @@ struct AzNet {
     float *fc_b = nullptr;       // [1]
     // bf16 tensor-core mode (az_net_tc.cu): BN scale folded into the weights, UMMA operand layout
     uint8_t *tc_stream = nullptr;      // [input conv | tower | heads] in the order the TMA producer streams them
+    uint8_t *tc_stream16 = nullptr;    // the same stream with IEEE-half operands (AZ_NET_F16)
     int tc_tiles = 2;                  // kernel variant: tiles (of 2 boards) per CTA
     int tc_cluster = 1;                // CTAs per cluster sharing one multicast weight stream
     __nv_bfloat16 *tc_w = nullptr;     // [2*blocks][18 chunks][8 kgroups][128 cout][8 cin]
@@ -40,11 +42,16 @@ struct AzNet {
 int az_net_tc_alloc(AzNet *net);
 int az_net_tc_prepare(az_context *ctx, AzNet *net);
 // `stream` = nullptr: the context stream; `tiles` = 0: the context's default kernel variant
+// d_exps / d_totals (optional): the kernel also writes exp((double)logit) [n][833] and their sequential sum [n]
 int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
-                      const int *d_count = nullptr, cudaStream_t stream = nullptr, int tiles = 0);
+                      const int *d_count = nullptr, cudaStream_t stream = nullptr, int tiles = 0, double *d_exps = nullptr,
+                      double *d_totals = nullptr, int f16 = 0, const int *d_out_map = nullptr);
+// mean over the 8 dihedral images of each of the n positions, one launch (nn_evals.py:48-62)
+int az_net_tc_forward_sym8(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values, int f16 = 0);
 // internal: forward over up to `n` boards; when d_count != nullptr the actual count is read on the device
 int az_net_forward_internal(az_context *ctx, const void *d_in, int in_kind, int n, int mode, float *d_logits, float *d_values,
-                            const int *d_count, cudaStream_t stream = nullptr, int tiles = 0);
+                            const int *d_count, cudaStream_t stream = nullptr, int tiles = 0, double *d_exps = nullptr,
+                            double *d_totals = nullptr, const int *d_out_map = nullptr);
 int az_net_tc_boards_per_round(az_context *ctx, int tiles);   // boards one wave of persistent CTAs evaluates
 void az_net_tc_release(AzNet *net);
 

@@ -1,3 +1,4 @@
+// AZ_NVCC_FLAGS: -fmad=false
 // az_net_tc.cu -- the conv tower as bf16 tcgen05 implicit GEMMs, whole network in ONE persistent
 // kernel (sm_100a).  Replaces TF1's sess.run of model.py:38-79 on the self-play hot path
 // (accelerated_generate_games.py:57-63) and the dead cuDNN stub cpp/fast_eval.cpp:37-126.
@@ -18,7 +19,16 @@
 //     1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx); each stage feeds both tiles.
 //   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (single elected lane), warps 2-5 /
 //     6-9 = epilogue of tile 0 / tile 1 (TMEM -> +shift, +residual, ReLU -> bf16 -> smem, and the
-//     heads' logits/value to HBM).
+//     heads' logits/value to HBM), last warp = softmax helper.
+//   * Softmax front half for the tree kernel (self_play_client.cpp:208-214), when the caller asks for it: the head
+//     epilogue also writes exp((double)logit) of all 833 logits, and the helper warp adds them up strictly left to
+//     right -- the reference's sequential `total +=` -- one lane per board, while the CTA is already busy with its
+//     next boards.  833 double exponentials and an 833-long dependent chain of double additions per leaf would
+//     otherwise saturate the fp64 pipes of the latency-bound tree kernel (16 games per SM start on them at once).
+//     This file is compiled without fused multiply-add contraction like az_tree.cu, so both produce the same bits.
+//   * Symmetry ensemble (nn_evals.py:48-62): in sym8 mode a CTA runs the 8 dihedral images of one position through the
+//     tower in four consecutive passes -- the images are generated while the input planes are staged and averaged
+//     (policies rotated back spatially, direction planes not permuted, as in the reference) in the head epilogue.
 #include "az_net.h"
 #include "az_rules.cuh"
 
@@ -72,11 +82,15 @@ struct Cfg {
     static constexpr int OFF_IN = OFF_ACT;
     static constexpr int OFF_SHIFT = OFF_RING + STAGES * STAGE_BYTES;   // float[TILES][2][F]: per-layer BN shifts, double-buffered
     static constexpr int OFF_VPART = OFF_SHIFT + TILES * 2 * F * 4;
-    static constexpr int OFF_BAR = OFF_VPART + 64;
+    static constexpr int OFF_SYM = OFF_VPART + 64;                   // sym8 mode: float[833] policy sum + float[8] values (+ pad)
+    static constexpr int SYM_BYTES = 3392;
+    static constexpr int OFF_BAR = OFF_SYM + SYM_BYTES;
     static constexpr int NUM_BARS = 2 * STAGES + (1 + SPLIT) * TILES + 1;   // full/empty ring, acc_full + SPLIT x act_ready per tile, input staged
     static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
     static constexpr int SMEM_BYTES = OFF_TMEM + 16;
-    static constexpr int NUM_WARPS = 2 + 4 * TILES;
+    static constexpr int NUM_WARPS = 3 + 4 * TILES;                 // producer, MMA issuer, 4 epilogue warps per tile, softmax helper
+    static constexpr int HELPER_WARP = 2 + 4 * TILES;
+    static constexpr int EPI_THREADS = 128 * TILES;
     static constexpr int NUM_THREADS = NUM_WARPS * 32;
     static constexpr int CTAS_PER_SM = TILES == 1 ? 2 : 1;
     static constexpr uint32_t TMEM_COLS = TILES * 256;             // per tile: 128 accumulator + 128 residual columns
@@ -86,9 +100,11 @@ struct Cfg {
 };
 
 // instruction descriptor: D=f32, A=B=bf16, K-major both, M=128, N
+// (A / B format fields, bits 7-9 / 10-12: 1 = bf16, 0 = f16 -- the AZ_NET_F16 mode clears both)
 constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24); }
 constexpr uint32_t IDESC_128 = make_idesc(128);
 constexpr uint32_t IDESC_HEAD = make_idesc(HEAD_N);
+constexpr uint32_t IDESC_FMT_BF16 = (1u << 7) | (1u << 10);
 
 // ------------------------------------------------------------------------------------------
 // PTX helpers
@@ -251,6 +267,28 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);
 }
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi)
+{
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) { return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi); }
+
+// 32 channels of one GEMM row -> four 16-byte k-group rows of the activation buffer, in the operand format
+template <bool F16>
+__device__ __forceinline__ void store_row(const uint32_t (&a)[32], uint8_t *dst, int lbo)
+{
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_op<F16>(__uint_as_float(a[8 * g + 0]), __uint_as_float(a[8 * g + 1]));
+        o.y = pack_op<F16>(__uint_as_float(a[8 * g + 2]), __uint_as_float(a[8 * g + 3]));
+        o.z = pack_op<F16>(__uint_as_float(a[8 * g + 4]), __uint_as_float(a[8 * g + 5]));
+        o.w = pack_op<F16>(__uint_as_float(a[8 * g + 6]), __uint_as_float(a[8 * g + 7]));
+        *reinterpret_cast<uint4 *>(dst + g * lbo) = o;
+    }
+}
 
 // named barrier among the 4 epilogue warps of one tile
 __device__ __forceinline__ void group_sync(int tile)
@@ -258,6 +296,40 @@ __device__ __forceinline__ void group_sync(int tile)
     // literal barrier ids so ptxas reserves 3 barriers, not all 16 (two CTAs share an SM in the 1-tile variant)
     if (tile == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
     else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+
+// exp((double)logit) exactly as the tree kernel computes it (az_tree.cu populate_from_eval): same libdevice routine, same
+// compiler flags.  Not inlined: 17 calls per epilogue thread and unit, off the layer-to-layer critical path.
+__device__ __noinline__ double exp_d(float x) { return exp((double)x); }
+
+// nn_evals.apply_symmetry (nn_evals.py:7-15): image[i][j] = board[a'][b'] with (a, b) = sym&4 ? (j, i) : (i, j),
+// b' = sym&2 ? 6-b : b, a' = sym&1 ? 6-a : a.  The same map takes an image cell to the board cell its policy belongs to
+// when the image was made with `sym` (applying inverse_symmetry[sym] to the output, nn_evals.py:27,58-61, undoes it).
+__device__ __forceinline__ int sym_cell(int sym, int i, int j)
+{
+    int a = (sym & 4) ? j : i, b = (sym & 4) ? i : j;
+    if (sym & 2) b = 6 - b;
+    if (sym & 1) a = 6 - a;
+    return a * 7 + b;
+}
+
+template <int TILES>
+__device__ __forceinline__ void epilogue_sync_all()       // all epilogue threads of the CTA (both tiles)
+{
+    if (TILES == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 4, 256;" ::: "memory");
+}
+template <int TILES>
+__device__ __forceinline__ void helper_arrive()           // epilogue threads -> softmax helper warp: "the exps of this unit are written"
+{
+    if (TILES == 1) asm volatile("bar.arrive 3, 160;" ::: "memory");
+    else asm volatile("bar.arrive 3, 288;" ::: "memory");
+}
+template <int TILES>
+__device__ __forceinline__ void helper_wait()
+{
+    if (TILES == 1) asm volatile("bar.sync 3, 160;" ::: "memory");
+    else asm volatile("bar.sync 3, 288;" ::: "memory");
 }
 
 struct TcParams {
@@ -273,6 +345,11 @@ struct TcParams {
     float *logits;                     // [n][833]
     float *values;                     // [n]
     float *debug_act;                  // [n][49][128] (debug only)
+    const int *out_map;                // when non-null: the outputs of board b go to row out_map[b] of values / exps / totals (logits too)
+    double *exps;                      // when non-null: [n][833] exp((double)logit), the softmax numerators of :210-211
+    double *totals;                    // [n] their strictly sequential sum (:212-214)
+    int f16;                           // operands (weights, activations) are IEEE half instead of bf16: 3 more mantissa bits, 5-bit exponent
+    int sym8;                          // 1: `n` positions, each evaluated as the mean over its 8 dihedral images (nn_evals.py:48-62)
     int experiment;                    // AZ_NET_EXPERIMENT bits: 1 = no weight copies (stale smem), 2 = no tower MMAs.  Wrong results; timing studies only.
 };
 
@@ -306,7 +383,10 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
     constexpr int B_FULL = 0, B_EMPTY = STAGES, B_ACC = 2 * STAGES, B_ACT = 2 * STAGES + TILES, B_IN = 2 * STAGES + (1 + SPLIT) * TILES;
 
     const int n_boards = P.n_ptr ? min(*P.n_ptr, P.n) : P.n;
-    const int num_units = ((n_boards + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS + CS - 1) / CS * CS;   // cluster peers run the same number of passes
+    // work items of a CTA: units of UNIT_BOARDS boards, or (sym8) whole positions, each `passes` trips through the tower
+    const int passes = P.sym8 ? 8 / C::UNIT_BOARDS : 1;
+    const int items = P.sym8 ? n_boards : (n_boards + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS;
+    const int num_units = (items + CS - 1) / CS * CS;              // cluster peers run the same number of passes
     const int tower_layers = P.layers - 1;          // tensor-core 128->128 convs
     const int run_layers = P.debug_layers >= 0 ? min(P.debug_layers, P.layers) : P.layers;   // conv layers executed (incl. input conv)
     const int nl = min(tower_layers, run_layers - 1);
@@ -351,17 +431,20 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
             };
             const uint8_t *tower = P.w_stream + WIN_BYTES;
             const uint8_t *head_w = tower + (size_t)tower_layers * CHUNKS * STAGE_BYTES;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                for (int j0 = 0; j0 < 5; j0 += WIN_KSTEPS_PER_STAGE)
-                    push(P.w_stream + j0 * WIN_KSTEP_BYTES, min(WIN_KSTEPS_PER_STAGE, 5 - j0) * WIN_KSTEP_BYTES);
-                for (int c = 0; c < nl * CHUNKS; ++c) push(tower + (size_t)c * STAGE_BYTES, STAGE_BYTES);
-                if (heads) push(head_w, WHEAD_BYTES);
-            }
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x)
+                for (int pass = 0; pass < passes; ++pass) {
+                    for (int j0 = 0; j0 < 5; j0 += WIN_KSTEPS_PER_STAGE)
+                        push(P.w_stream + j0 * WIN_KSTEP_BYTES, min(WIN_KSTEPS_PER_STAGE, 5 - j0) * WIN_KSTEP_BYTES);
+                    for (int c = 0; c < nl * CHUNKS; ++c) push(tower + (size_t)c * STAGE_BYTES, STAGE_BYTES);
+                    if (heads) push(head_w, WHEAD_BYTES);
+                }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
         if (elect_one()) {
             uint32_t it = 0, in_phase = 0, act_phase = 0;
+            const uint32_t idesc_128 = P.f16 ? (IDESC_128 & ~IDESC_FMT_BF16) : IDESC_128;
+            const uint32_t idesc_head = P.f16 ? (IDESC_HEAD & ~IDESC_FMT_BF16) : IDESC_HEAD;
             auto acquire = [&]() {               // wait for the next stage of the weight stream
                 const int s = it % STAGES;
                 mbar_wait(bar(B_FULL + s), (it / STAGES) & 1);
@@ -373,7 +456,8 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                 else umma_commit_multicast(bar(B_EMPTY + s), CMASK);
             };
             auto release = [&]() { free_stage(it % STAGES); ++it; };
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x)
+            for (int pass = 0; pass < passes; ++pass) {
                 // ---- input conv: 9 taps x 8 (4 real) channels, two taps per K=16 step ----
                 mbar_wait(bar(B_IN), in_phase);
                 in_phase ^= 1;
@@ -389,7 +473,7 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                             // the 10th "tap" has all-zero weights: any finite rows will do, take the next row
                             const uint32_t a1 = tap1 < 9 ? in_rows + ((tap1 / 3 - 1) * 8 + (tap1 % 3 - 1)) * ROW_BYTES : a0 + ROW_BYTES;
                             umma(tmem_base + C::TM_ACC + t * 128, make_desc(a0, a1 - a0), make_desc(b_rows + (j - j0) * 2 * W_LBO, W_LBO),
-                                 IDESC_128, j > 0);
+                                 idesc_128, j > 0);
                         }
                         if (j1 == 5) umma_commit(bar(B_ACC + t));
                     }
@@ -424,7 +508,7 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                             for (int t = 0; t < TILES; ++t) {           // every weight stage feeds all of the CTA's tiles
 #pragma unroll
                                 for (int j = 0; j < PART_MMAS; ++j)
-                                    umma_lo(d_col + t * 128, a_lo + t * TILE_M + j * A_KSTEP, a_hi, b_lo + j * B_KSTEP, b_hi, IDESC_128,
+                                    umma_lo(d_col + t * 128, a_lo + t * TILE_M + j * A_KSTEP, a_hi, b_lo + j * B_KSTEP, b_hi, idesc_128,
                                             onto_res | (uint32_t)((part | tap | j) != 0));
                                 if (part == SPLIT - 1 && tap == 8) umma_commit(bar(B_ACC + t));
                             }
@@ -446,10 +530,76 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             umma(tmem_base + C::TM_ACC + t * 128, make_desc(a_rows + 2 * j * C::ACT_LBO, C::ACT_LBO),
-                                 make_desc(b_rows + 2 * j * HEAD_LBO, HEAD_LBO), IDESC_HEAD, j > 0);
+                                 make_desc(b_rows + 2 * j * HEAD_LBO, HEAD_LBO), idesc_head, j > 0);
                         umma_commit(bar(B_ACC + t));
                     }
                     release();
+                }
+            }
+        }
+    } else if (warp == C::HELPER_WARP) {
+        // =============================== softmax helper ===============================
+        // total = sum_i exp(logit_i), i ascending, added one by one in double (self_play_client.cpp:212-214): one lane per
+        // board of the unit the epilogue warps have just finished; they are already working on the next one.
+        // All 32 lanes fetch the numerators chunk by chunk (coalesced, the next chunk in flight while the current one is
+        // being added) into a small shared-memory stage; lane b then walks board b's chunk in order.  The chain of 833
+        // dependent additions per board (~8 clocks each) is all that remains on the kernel's tail after the last unit.
+        if (heads && P.exps && !P.sym8) {
+            constexpr int CH = 96;                                  // doubles per board and chunk: 3 per lane
+            constexpr int NCH = (AZ_LOGITS + CH - 1) / CH;
+            double *stage = reinterpret_cast<double *>(smem + C::OFF_SYM);       // [UNIT_BOARDS][CH] (the sym8 area is free here)
+            static_assert(C::UNIT_BOARDS * CH * 8 <= C::SYM_BYTES, "softmax stage fits the sym8 area");
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                helper_wait<TILES>();
+                const double *e[C::UNIT_BOARDS];
+                int ob[C::UNIT_BOARDS];
+#pragma unroll
+                for (int b = 0; b < C::UNIT_BOARDS; ++b) {
+                    const int board = unit * C::UNIT_BOARDS + b;
+                    ob[b] = board < n_boards ? (P.out_map ? __ldg(P.out_map + board) : board) : -1;
+                    e[b] = P.exps + (size_t)max(ob[b], 0) * AZ_LOGITS;
+                }
+                double v[C::UNIT_BOARDS][3];
+                auto fetch = [&](int c) {
+#pragma unroll
+                    for (int b = 0; b < C::UNIT_BOARDS; ++b)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const int i = c * CH + lane + 32 * j;
+                            v[b][j] = (ob[b] >= 0 && i < AZ_LOGITS) ? __ldcg(e[b] + i) : 0.0;
+                        }
+                };
+                double total = 0.0;
+                fetch(0);
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                    for (int b = 0; b < C::UNIT_BOARDS; ++b)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) stage[b * CH + lane + 32 * j] = v[b][j];
+                    __syncwarp();
+                    if (c + 1 < NCH) fetch(c + 1);
+                    if (lane < C::UNIT_BOARDS) {
+                        const double *row = stage + lane * CH;
+                        const int count = min(CH, AZ_LOGITS - c * CH);
+                        int i = 0;
+                        for (; i + 8 <= count; i += 8) {
+                            const double2 a = *reinterpret_cast<const double2 *>(row + i), b2 = *reinterpret_cast<const double2 *>(row + i + 2);
+                            const double2 c2 = *reinterpret_cast<const double2 *>(row + i + 4), d2 = *reinterpret_cast<const double2 *>(row + i + 6);
+                            total = __dadd_rn(total, a.x); total = __dadd_rn(total, a.y);
+                            total = __dadd_rn(total, b2.x); total = __dadd_rn(total, b2.y);
+                            total = __dadd_rn(total, c2.x); total = __dadd_rn(total, c2.y);
+                            total = __dadd_rn(total, d2.x); total = __dadd_rn(total, d2.y);
+                        }
+                        for (; i < count; ++i) total = __dadd_rn(total, row[i]);
+                    }
+                    __syncwarp();
+                }
+                if (lane < C::UNIT_BOARDS) {
+                    int mine = -1;
+#pragma unroll
+                    for (int b = 0; b < C::UNIT_BOARDS; ++b) mine = lane == b ? ob[b] : mine;
+                    if (mine >= 0) P.totals[mine] = total;
                 }
             }
         }
@@ -467,24 +617,29 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
         uint8_t *act_row = smem + C::OFF_ACT + (MARGIN + tile * TILE_M + r) * ROW_BYTES;
         uint32_t acc_phase = 0;
 
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-            const int board = unit * C::UNIT_BOARDS + tile * 2 + bit;
+        float *sym_acc = reinterpret_cast<float *>(smem + C::OFF_SYM);       // sym8 mode: policy sum [833], then the 8 values
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x)
+        for (int pass = 0; pass < passes; ++pass) {
+            // normal mode: the unit's boards; sym8 mode: position `unit`, image sym = pass * UNIT_BOARDS + (row's board in the unit)
+            const int sym = P.sym8 ? pass * C::UNIT_BOARDS + tile * 2 + bit : 0;
+            const int board = P.sym8 ? unit : unit * C::UNIT_BOARDS + tile * 2 + bit;
             const bool live = real && board < n_boards;
             // ---- stage the input planes of this row: 4 feature channels + 4 zeros, bf16 ----
             {
                 uint4 v = make_uint4(0, 0, 0, 0);
                 if (live) {
                     float f[4];
+                    const int src_cell = P.sym8 ? sym_cell(sym, cell / 7, cell % 7) : cell;    // the image's cell shows this board cell
                     if (IN_KIND == AZ_IN_F32) {
-                        const float4 q = reinterpret_cast<const float4 *>(P.input)[(size_t)board * 49 + cell];
+                        const float4 q = reinterpret_cast<const float4 *>(P.input)[(size_t)board * 49 + src_cell];
                         f[0] = q.x; f[1] = q.y; f[2] = q.z; f[3] = q.w;
                     } else {
                         az_position p = reinterpret_cast<const az_position *>(P.input)[board];
                         p.turn &= 1;
-                        az::feature_cell(p, cell / 7, cell % 7, f);
+                        az::feature_cell(p, src_cell / 7, src_cell % 7, f);
                     }
-                    v.x = pack_bf16(f[0], f[1]);
-                    v.y = pack_bf16(f[2], f[3]);
+                    v.x = P.f16 ? pack_f16(f[0], f[1]) : pack_bf16(f[0], f[1]);
+                    v.y = P.f16 ? pack_f16(f[2], f[3]) : pack_bf16(f[2], f[3]);
                 }
                 *reinterpret_cast<uint4 *>(smem + C::OFF_IN + (MARGIN + tile * TILE_M + r) * ROW_BYTES) = v;
                 fence_proxy_async();
@@ -517,15 +672,8 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                         a[i] = __float_as_uint(v);
                     }
                     if (writes_res) tmem_st32(lane_addr + C::TM_RES + tile * 128 + q * 32, a);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint4 o;
-                        o.x = pack_bf16(__uint_as_float(a[8 * g + 0]), __uint_as_float(a[8 * g + 1]));
-                        o.y = pack_bf16(__uint_as_float(a[8 * g + 2]), __uint_as_float(a[8 * g + 3]));
-                        o.z = pack_bf16(__uint_as_float(a[8 * g + 4]), __uint_as_float(a[8 * g + 5]));
-                        o.w = pack_bf16(__uint_as_float(a[8 * g + 6]), __uint_as_float(a[8 * g + 7]));
-                        *reinterpret_cast<uint4 *>(act_row + (q * 4 + g) * C::ACT_LBO) = o;
-                    }
+                    if (P.f16) store_row<true>(a, act_row + q * 4 * C::ACT_LBO, C::ACT_LBO);
+                    else store_row<false>(a, act_row + q * 4 * C::ACT_LBO, C::ACT_LBO);
                     if (P.debug_layers >= 0 && l == run_layers - 1 && live) {
                         float *dst = P.debug_act + ((size_t)board * 49 + cell) * F + q * 32;
                         for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(a[i]);
@@ -553,10 +701,13 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                 tmem_ld32(lane_addr + C::TM_ACC + tile * 128, a);
                 tmem_wait_ld();
                 float vterm = 0.f;
+                const int ob = (P.out_map && board < n_boards) ? __ldg(P.out_map + board) : board;     // output row of this board
                 if (live) {
-                    float *dst = P.logits + (size_t)board * AZ_LOGITS + cell * 17;
+                    if (!P.sym8 && P.logits) {
+                        float *dst = P.logits + (size_t)ob * AZ_LOGITS + cell * 17;
 #pragma unroll
-                    for (int i = 0; i < 17; ++i) dst[i] = __uint_as_float(a[i]);
+                        for (int i = 0; i < 17; ++i) dst[i] = __uint_as_float(a[i]);
+                    }
                     vterm = __uint_as_float(a[17]) * __ldg(P.fc_w + cell);
                 }
                 // value head: sum over the board's 49 cells (one board = 2 warps), then tanh
@@ -566,10 +717,52 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
                 tc_fence_before();
                 group_sync(tile);
                 if (gtid < 2) {
-                    const int b = unit * C::UNIT_BOARDS + tile * 2 + gtid;
-                    if (b < n_boards) P.values[b] = tanhf(vpart[2 * gtid] + vpart[2 * gtid + 1] + __ldg(P.fc_b));
+                    const float value = tanhf(vpart[2 * gtid] + vpart[2 * gtid + 1] + __ldg(P.fc_b));
+                    if (P.sym8) {
+                        sym_acc[AZ_LOGITS + pass * C::UNIT_BOARDS + tile * 2 + gtid] = value;
+                    } else {
+                        const int b = unit * C::UNIT_BOARDS + tile * 2 + gtid;
+                        if (b < n_boards) P.values[P.out_map ? __ldg(P.out_map + b) : b] = value;
+                    }
                 }
-                group_sync(tile);
+                if (P.sym8) {
+                    // mean over the 8 images, each rotated back onto the board (spatially only: the 16 direction planes are
+                    // not permuted, nn_evals.py:58-62).  Images are added in ascending order (np.mean's order for axis 0), one
+                    // image at a time: an image is a permutation of the cells, so its rows never collide.
+                    const int my_image = tile * 2 + bit;
+                    const int dst_cell = sym_cell(sym, cell / 7, cell % 7);
+                    for (int im = 0; im < C::UNIT_BOARDS; ++im) {
+                        if (im == my_image && live) {
+                            float *dst = sym_acc + dst_cell * 17;
+#pragma unroll
+                            for (int i = 0; i < 17; ++i) dst[i] = sym == 0 ? __uint_as_float(a[i]) : dst[i] + __uint_as_float(a[i]);
+                        }
+                        epilogue_sync_all<TILES>();
+                    }
+                    if (pass == passes - 1) {
+                        const int t_all = tile * 128 + gtid;
+                        if (board < n_boards) {
+                            for (int i = t_all; i < AZ_LOGITS; i += C::EPI_THREADS) P.logits[(size_t)board * AZ_LOGITS + i] = sym_acc[i] * 0.125f;
+                            if (t_all == 0) {
+                                const float *v = sym_acc + AZ_LOGITS;       // np.mean of 8 floats: numpy's pairwise tree
+                                P.values[board] = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) * 0.125f;
+                            }
+                        }
+                        epilogue_sync_all<TILES>();      // the sum is read before the next position overwrites it
+                    }
+                } else if (P.exps) {
+                    // softmax numerators in double for the tree kernel; the helper warp adds them up
+                    if (live) {
+                        double *e = P.exps + (size_t)ob * AZ_LOGITS + cell * 17;
+#pragma unroll
+                        for (int i = 0; i < 17; ++i) e[i] = exp_d(__uint_as_float(a[i]));
+                    }
+                    __threadfence_block();
+                    helper_arrive<TILES>();
+                    group_sync(tile);
+                } else {
+                    group_sync(tile);
+                }
             }
         }
     }
@@ -588,8 +781,15 @@ __global__ void __launch_bounds__(Cfg<TILES>::NUM_THREADS, Cfg<TILES>::CTAS_PER_
 namespace {
 // Re-tile the fp32 TF-layout parameters into the UMMA operand images the kernel streams, folding the
 // batch-norm scale 1/sqrt(var+eps) of the conv's own BN layer into its output channels.
+__device__ __forceinline__ uint16_t to_operand(float w, int f16)
+{
+    if (f16) { const __half h = __float2half_rn(w); return *reinterpret_cast<const uint16_t *>(&h); }
+    const __nv_bfloat16 b = __float2bfloat16_rn(w);
+    return *reinterpret_cast<const uint16_t *>(&b);
+}
+
 __global__ void k_tile_tower(const float *__restrict__ w_tower, const float *__restrict__ scale, int tower_layers,
-                             __nv_bfloat16 *__restrict__ out)
+                             uint16_t *__restrict__ out, int f16)
 {
     // out index: ((((l*CHUNKS + chunk)*PART_KG + kg)*128 + co)*8 + i), chunk = part*9 + tap
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -604,12 +804,12 @@ __global__ void k_tile_tower(const float *__restrict__ w_tower, const float *__r
     const int part = chunk / 9, tap = chunk % 9;
     const int cin = (part * PART_KG + kg) * 8 + i;
     const float w = w_tower[(((size_t)l * 9 + tap) * F + cin) * F + co] * scale[(size_t)(l + 1) * F + co];
-    out[idx] = __float2bfloat16_rn(w);
+    out[idx] = to_operand(w, f16);
 }
 
 __global__ void k_tile_small(const float *__restrict__ w_in, const float *__restrict__ w_policy, const float *__restrict__ w_value,
                              const float *__restrict__ bn_raw, const float *__restrict__ scale, int layers,
-                             __nv_bfloat16 *__restrict__ out_in, __nv_bfloat16 *__restrict__ out_heads, float *__restrict__ shift)
+                             uint16_t *__restrict__ out_in, uint16_t *__restrict__ out_heads, float *__restrict__ shift, int f16)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < 5 * 2 * F * 8) {                   // input conv: [kstep j][g][cout][i], tap = 2j+g (tap 9 = zero), 4 real channels
@@ -617,7 +817,7 @@ __global__ void k_tile_small(const float *__restrict__ w_in, const float *__rest
         const int tap = 2 * j + g;
         float w = 0.f;
         if (tap < 9 && i < 4) w = w_in[((size_t)tap * 4 + i) * F + co] * scale[co];
-        out_in[idx] = __float2bfloat16_rn(w);
+        out_in[idx] = to_operand(w, f16);
     }
     if (idx < KG * HEAD_N * 8) {                 // heads: [kg][row 0..31][i]: rows 0..16 policy planes, row 17 value plane
         const int i = idx & 7, row = (idx >> 3) & 31, kg = idx >> 8;
@@ -625,7 +825,7 @@ __global__ void k_tile_small(const float *__restrict__ w_in, const float *__rest
         float w = 0.f;
         if (row < 17) w = w_policy[(size_t)cin * 17 + row];
         else if (row == 17) w = w_value[cin];
-        out_heads[idx] = __float2bfloat16_rn(w);
+        out_heads[idx] = to_operand(w, f16);
     }
     if (idx < layers * F) {                      // epilogue shift = -mean * scale, in double like the reference's BN
         const int l = idx / F, c = idx % F;
@@ -637,9 +837,10 @@ __global__ void k_tile_small(const float *__restrict__ w_in, const float *__rest
 
 int az_net_tc_alloc(AzNet *net)
 {
-    // one contiguous weight stream: [input conv][tower][heads], exactly the order the producer walks
+    // one contiguous weight stream per operand format: [input conv][tower][heads], exactly the order the producer walks
     const size_t tower = (size_t)2 * net->blocks * CHUNKS * STAGE_BYTES;
     AZ_CUDA(cudaMalloc(&net->tc_stream, WIN_BYTES + tower + WHEAD_BYTES));
+    AZ_CUDA(cudaMalloc(&net->tc_stream16, WIN_BYTES + tower + WHEAD_BYTES));
     net->tc_w_in = reinterpret_cast<__nv_bfloat16 *>(net->tc_stream);
     net->tc_w = reinterpret_cast<__nv_bfloat16 *>(net->tc_stream + WIN_BYTES);
     net->tc_w_heads = reinterpret_cast<__nv_bfloat16 *>(net->tc_stream + WIN_BYTES + tower);
@@ -660,10 +861,16 @@ int az_net_tc_prepare(az_context *ctx, AzNet *net)
 {
     cudaStream_t s = ctx->stream;
     const size_t tower = (size_t)2 * net->blocks * CHUNKS * PART_KG * F * 8;
-    k_tile_tower<<<(unsigned)((tower + 255) / 256), 256, 0, s>>>(net->w_tower, net->bn_scale, 2 * net->blocks, net->tc_w);
+    const size_t tower_bytes = (size_t)2 * net->blocks * CHUNKS * STAGE_BYTES;
     const int small = std::max(std::max(5 * 2 * F * 8, KG * HEAD_N * 8), net->layers * F);
-    k_tile_small<<<(small + 255) / 256, 256, 0, s>>>(net->w_in, net->w_policy, net->w_value, net->bn_raw, net->bn_scale, net->layers,
-                                                     net->tc_w_in, net->tc_w_heads, net->tc_shift);
+    for (int f16 = 0; f16 < 2; ++f16) {              // the same tiling in both operand formats (bf16: AZ_NET_BF16, half: AZ_NET_F16)
+        uint8_t *base = f16 ? net->tc_stream16 : net->tc_stream;
+        k_tile_tower<<<(unsigned)((tower + 255) / 256), 256, 0, s>>>(net->w_tower, net->bn_scale, 2 * net->blocks,
+                                                                     reinterpret_cast<uint16_t *>(base + WIN_BYTES), f16);
+        k_tile_small<<<(small + 255) / 256, 256, 0, s>>>(net->w_in, net->w_policy, net->w_value, net->bn_raw, net->bn_scale, net->layers,
+                                                         reinterpret_cast<uint16_t *>(base), reinterpret_cast<uint16_t *>(base + WIN_BYTES + tower_bytes),
+                                                         net->tc_shift, f16);
+    }
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
@@ -671,6 +878,8 @@ int az_net_tc_prepare(az_context *ctx, AzNet *net)
 void az_net_tc_release(AzNet *net)
 {
     if (net->tc_stream) cudaFree(net->tc_stream);
+    if (net->tc_stream16) cudaFree(net->tc_stream16);
+    net->tc_stream16 = nullptr;
     if (net->tc_shift) cudaFree(net->tc_shift);
     net->tc_stream = nullptr;
     net->tc_w = net->tc_w_in = net->tc_w_heads = nullptr;
@@ -701,7 +910,7 @@ template <int TILES>
 static void tc_launch_variant(az_context *ctx, const TcParams &P, int in_kind, int n, cudaStream_t stream, int cluster)
 {
     using C = Cfg<TILES>;
-    const int units = (n + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS;
+    const int units = P.sym8 ? n : (n + C::UNIT_BOARDS - 1) / C::UNIT_BOARDS;     // sym8: one work item per position
     int slots = ctx->sm_count * C::CTAS_PER_SM;
     if (const char *env = getenv("AZ_NET_MAX_CTAS")) slots = std::max(1, std::min(slots, atoi(env)));     // experiment knob
     int grid = units < slots ? units : slots;
@@ -726,7 +935,8 @@ int az_net_tc_boards_per_round(az_context *ctx, int tiles)
 }
 
 static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
-                     int debug_layers, float *d_debug, const int *d_count = nullptr, cudaStream_t stream = nullptr, int tiles = 0)
+                     int debug_layers, float *d_debug, const int *d_count = nullptr, cudaStream_t stream = nullptr, int tiles = 0,
+                     double *d_exps = nullptr, double *d_totals = nullptr, int sym8 = 0, int f16 = 0, const int *d_out_map = nullptr)
 {
     if (!stream) stream = ctx->stream;
     if (tiles == 0) tiles = net->tc_tiles;
@@ -736,13 +946,18 @@ static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind,
     P.n_ptr = d_count;
     P.layers = net->layers;
     P.debug_layers = debug_layers;
-    P.w_stream = net->tc_stream;
+    P.w_stream = f16 ? net->tc_stream16 : net->tc_stream;
+    P.f16 = f16;
     P.shift = net->tc_shift;
     P.fc_w = net->fc_w;
     P.fc_b = net->fc_b;
     P.logits = d_logits;
     P.values = d_values;
     P.debug_act = d_debug;
+    P.out_map = d_out_map;
+    P.exps = d_exps;
+    P.totals = d_totals;
+    P.sym8 = sym8;
     static const int experiment = getenv("AZ_NET_EXPERIMENT") ? atoi(getenv("AZ_NET_EXPERIMENT")) : 0;
     P.experiment = experiment;
     if (tiles == 1) tc_launch_variant<1>(ctx, P, in_kind, n, stream, net->tc_cluster);
@@ -753,9 +968,15 @@ static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind,
 }
 
 int az_net_tc_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values,
-                      const int *d_count, cudaStream_t stream, int tiles)
+                      const int *d_count, cudaStream_t stream, int tiles, double *d_exps, double *d_totals, int f16, const int *d_out_map)
 {
-    return tc_launch(ctx, net, d_in, in_kind, n, d_logits, d_values, -1, nullptr, d_count, stream, tiles);
+    return tc_launch(ctx, net, d_in, in_kind, n, d_logits, d_values, -1, nullptr, d_count, stream, tiles, d_exps, d_totals, 0, f16, d_out_map);
+}
+
+// nn_evals.evaluate for n positions in ONE launch: images generated in the input staging, averaged in the head epilogue
+int az_net_tc_forward_sym8(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values, int f16)
+{
+    return tc_launch(ctx, net, d_in, in_kind, n, d_logits, d_values, -1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 1, f16);
 }
 
 // Debug/validation hook (not part of the public header): run the first `conv_layers` convolutions of the

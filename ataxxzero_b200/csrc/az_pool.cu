@@ -119,6 +119,7 @@ int launch_tree(az_pool *pool, Group &grp, bool consume = true)
     else AZ_CUDA(cudaMemsetAsync(grp.dev.req_count + 2 * grp.slot + 1, 0, sizeof(int32_t), s));   // top-up: same slot, fresh busy count
     grp.dev.consume = consume ? 1 : 0;
     grp.dev.tick_slot = grp.slot;
+    grp.dev.tick_id++;
     aztree_launch_tick(grp.dev, s);
     pool->launches++;
     pool->ctx->launches++;
@@ -128,8 +129,14 @@ int launch_tree(az_pool *pool, Group &grp, bool consume = true)
 
 int launch_net(az_pool *pool, Group &grp)
 {
-    int rc = az_net_forward_internal(pool->ctx, grp.dev.req_pos, AZ_IN_POS, grp.dev.cap, pool->cfg.eval_mode, grp.dev.logits,
-                                     grp.dev.values, grp.dev.req_count + 2 * grp.slot, grp.stream, pool->net_tiles);
+    const PoolDev &D = grp.dev;
+    int rc;
+    if (D.cache_tag)      // speculative search pool: every evaluation of the batch lands in its cache entry
+        rc = az_net_forward_internal(pool->ctx, D.req_pos, AZ_IN_POS, D.req_cap, pool->cfg.eval_mode, nullptr, D.cache_val,
+                                     D.req_count + 2 * grp.slot, grp.stream, pool->net_tiles, D.cache_exps, D.cache_tot, D.req_out);
+    else
+        rc = az_net_forward_internal(pool->ctx, D.req_pos, AZ_IN_POS, D.cap, pool->cfg.eval_mode, D.logits, D.values,
+                                     D.req_count + 2 * grp.slot, grp.stream, pool->net_tiles, D.exps, D.totals);
     pool->launches++;
     return rc;
 }
@@ -239,7 +246,8 @@ int drain_finished(az_pool *pool, Group &grp, FILE *out, int64_t *games_written,
 void free_group(Group &grp)
 {
     PoolDev &D = grp.dev;
-    void *ptrs[] = {D.nodes, D.games, D.path, D.gstack, D.req_pos, D.req_game, D.req_count, D.logits, D.values, D.records,
+    void *ptrs[] = {D.nodes, D.games, D.path, D.gstack, D.req_pos, D.req_game, D.req_count, D.logits, D.values, D.exps, D.totals, D.cache_tag,
+                    D.cache_exps, D.cache_tot, D.cache_val, D.req_out, D.records,
                     D.done, D.done_count, grp.d_done_snapshot, grp.d_status, grp.d_features, grp.d_offsets, grp.d_stage};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -270,7 +278,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
     *out = nullptr;
     AZ_REQUIRE(cfg->games >= 1 && cfg->games <= (1 << 20), AZ_ERR_ARG, "az_pool_create: games=%d", cfg->games);
     AZ_REQUIRE(cfg->visits >= 1 && cfg->visits <= (1 << 22), AZ_ERR_ARG, "az_pool_create: visits=%d", cfg->visits);
-    AZ_REQUIRE(cfg->eval_mode == AZ_NET_FP32 || cfg->eval_mode == AZ_NET_BF16 || cfg->eval_mode == AZ_EVAL_EXTERNAL, AZ_ERR_ARG,
+    AZ_REQUIRE(cfg->eval_mode == AZ_NET_FP32 || cfg->eval_mode == AZ_NET_BF16 || cfg->eval_mode == AZ_NET_F16 || cfg->eval_mode == AZ_EVAL_EXTERNAL, AZ_ERR_ARG,
                "az_pool_create: eval_mode=%d", cfg->eval_mode);
     AZ_REQUIRE(cfg->eval_mode == AZ_EVAL_EXTERNAL || ctx->net, AZ_ERR_STATE, "az_pool_create: no weights loaded (az_net_load)");
     az_position start;
@@ -287,7 +295,8 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
 
     // Self-play on the internal tensor-core net: two groups that take turns on the net kernel (see Group).  The
     // 2-tile net variant (one CTA per SM) is used there because it leaves room for the tree blocks on every SM.
-    const bool pipelined = cfg->auto_play && cfg->eval_mode == AZ_NET_BF16;
+    const bool tensor_net = cfg->eval_mode == AZ_NET_BF16 || cfg->eval_mode == AZ_NET_F16;
+    const bool pipelined = cfg->auto_play && tensor_net;
     int n_groups = 1;
     if (pipelined) {
         const char *env = getenv("AZ_POOL_GROUPS");
@@ -369,6 +378,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         D.seed = cfg->seed;
         D.tick_cycles = getenv("AZ_TICK_CYCLES") ? atoi(getenv("AZ_TICK_CYCLES")) : 0;
         D.force_slow = getenv("AZ_TREE_FORCE_SLOW") ? atoi(getenv("AZ_TREE_FORCE_SLOW")) : 0;
+        D.favourite = getenv("AZ_TREE_FAVOURITE") ? atoi(getenv("AZ_TREE_FAVOURITE")) : 1;
         D.rec_cap_words = rec_cap_words;
         const size_t G = (size_t)D.G;
         rc |= dev_alloc(&D.nodes, G * D.C * kNodeStride, false);
@@ -380,6 +390,27 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         rc |= dev_alloc(&D.req_count, 8);
         rc |= dev_alloc(&D.logits, G * AZ_LOGITS);
         rc |= dev_alloc(&D.values, G);
+        const int spec_k = (tensor_net && !cfg->auto_play) ? std::min(std::max(cfg->speculate, 0), 64) : 0;
+        if (spec_k > 0) {
+            // speculative evaluation: a per-game cache of evaluations + a request batch that can hold the extra requests
+            int entries = 1024;
+            while (entries < 2 * pool->cfg.node_capacity && entries < (1 << 18)) entries *= 2;    // 6.7 KB per entry
+            D.cache_entries = entries;
+            D.spec_k = spec_k;
+            D.req_cap = std::max(2 * az_net_tc_boards_per_round(ctx, pool->net_tiles), (int)G * (1 + spec_k));
+            const size_t total = G * (size_t)entries + 1;        // + the trash entry
+            rc |= dev_alloc(&D.cache_tag, total);
+            rc |= dev_alloc(&D.cache_exps, total * AZ_LOGITS, false);
+            rc |= dev_alloc(&D.cache_tot, total, false);
+            rc |= dev_alloc(&D.cache_val, total, false);
+            rc |= dev_alloc(&D.req_out, (size_t)D.req_cap);
+            cudaFree(D.req_pos);
+            D.req_pos = nullptr;
+            rc |= dev_alloc(&D.req_pos, (size_t)std::max<int>(D.req_cap, (int)G));
+        } else if (tensor_net && !getenv("AZ_TREE_SOFTMAX")) {     // the net kernel delivers the softmax front half
+            rc |= dev_alloc(&D.exps, G * AZ_LOGITS);
+            rc |= dev_alloc(&D.totals, G);
+        }
         rc |= dev_alloc(&D.records, G * 2 * D.rec_cap_words, false);
         rc |= dev_alloc(&D.done, 2 * G);
         rc |= dev_alloc(&D.done_count, 1);
@@ -434,6 +465,25 @@ extern "C" void az_pool_destroy(az_pool *pool)
                         sum / grp.dev.G / std::max<uint64_t>(pool->ticks, 1) / 1e3, mx / std::max<uint64_t>(pool->ticks, 1) / 1e3,
                         (unsigned long long)pool->ticks);
             }
+            // the last tick on the wall clock: when did each game start and finish inside the kernel?
+            std::vector<double> start, finish;
+            unsigned long long t0 = ~0ull;
+            for (int g = 0; g < grp.dev.G; ++g)
+                if (h[(size_t)g * 8 + 6]) t0 = std::min(t0, h[(size_t)g * 8 + 6]);
+            for (int g = 0; g < grp.dev.G; ++g)
+                if (h[(size_t)g * 8 + 6]) {
+                    start.push_back((double)(h[(size_t)g * 8 + 6] - t0) * 1e-3);
+                    finish.push_back((double)(h[(size_t)g * 8 + 7] - t0) * 1e-3);
+                }
+            if (!finish.empty()) {
+                std::sort(start.begin(), start.end());
+                std::sort(finish.begin(), finish.end());
+                auto pct = [](const std::vector<double> &v, double q) { return v[std::min(v.size() - 1, (size_t)(q * v.size()))]; };
+                fprintf(stderr, "[az_pool profile] last tick, us after the first warp started: starts p50 %.1f p99 %.1f max %.1f | finishes p10 %.1f "
+                                "p50 %.1f p75 %.1f p87 %.1f p95 %.1f p99 %.1f max %.1f\n",
+                        pct(start, 0.5), pct(start, 0.99), start.back(), pct(finish, 0.10), pct(finish, 0.5), pct(finish, 0.75), pct(finish, 0.87),
+                        pct(finish, 0.95), pct(finish, 0.99), finish.back());
+            }
             cudaFree(grp.dev.prof);
             grp.dev.prof = nullptr;
         }
@@ -461,6 +511,7 @@ extern "C" int az_pool_stats_get(az_pool *pool, az_pool_stats *out)
             s.games_finished += g.finished;
             s.games_skipped += g.skipped;
             s.max_depth = std::max<uint64_t>(s.max_depth, g.max_depth);
+            s.levels += g.levels;
         }
     }
     s.ticks = pool->ticks;

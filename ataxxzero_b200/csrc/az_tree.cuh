@@ -45,6 +45,7 @@ constexpr int kHintShift = 23;
 constexpr uint32_t kChildMask = 0x00ffffffu;     // Entry::child: node index
 constexpr int kMoveIdxShift = 24;
 constexpr int kNoCand = 0xff;
+constexpr uint32_t kFavValid = 0x80000000u;
 constexpr int kRecWordsPerPly = 6 + 2 * 256;    // worst-case record words per ply
 
 enum : uint32_t {
@@ -68,8 +69,11 @@ struct __align__(16) NodeHdr {
     uint8_t turn;            // absolute side to move: 0 = x, 1 = o
     uint8_t flags;
     uint16_t pad0;
-    uint32_t pad[3];
+    uint32_t pad[1];
+    uint32_t fav;            // node index of the child the last selection at this node went to | kFavValid ("favourite":
+    uint32_t fav_k;          // fetched before the scores are known) and the number of entries that child had
 };
+constexpr int kOffFav = 56;
 static_assert(sizeof(NodeHdr) == 64, "node header is 64 bytes");
 
 struct Entry {
@@ -98,8 +102,22 @@ struct __align__(16) Game {
     uint64_t start_own, start_opp;    // starting position of this slot (side to move / opponent)
     // statistics (summed by the host on demand)
     unsigned long long steps, evals, terminal_steps, positions, finished, skipped, max_depth;
-    int32_t pad2[2];
+    unsigned long long levels;        // tree levels walked by completed selections (sum of path lengths)
 };
+
+// Search pools on the tensor-core net may evaluate SPECULATIVELY (az_pool_config::speculate, engine.py:387-392 queues the
+// likely children of a new node the same way): every game owns a small set-associative cache of evaluations keyed by the
+// exact position.  Expanding a move first looks its position up; the children with the largest priors of every node whose
+// evaluation is consumed are requested in the same batch.  An evaluation is a pure function of the position, so a hit
+// changes WHEN a leaf is linked, never what the search computes.
+struct __align__(16) CacheTag {
+    uint64_t own, opp;       // position: pieces of the side to move / of the opponent (blockers are fixed per game)
+    uint32_t turn;           // absolute side to move
+    uint32_t tick;           // tick in which the evaluation was requested: usable from the next tick on
+    uint32_t valid;
+    uint32_t pad;
+};
+constexpr int kCacheWays = 4;   // tags of one set share a 128-byte line
 
 struct DoneEntry {
     int32_t game, buf, words, plies, result, pad[3];
@@ -117,6 +135,8 @@ struct PoolDev {
                              // the first `cap` were evaluated) and zeroes its successor's slot, so the host never memsets.
     float *logits;           // [G][833]
     float *values;           // [G]
+    double *exps;            // [G][833] exp((double)logit), written by the tensor-core net kernel together with ...
+    double *totals;          // [G]      ... their sequential sum; nullptr: the tree kernel computes both itself
     uint32_t *records;       // [G][2][rec_cap_words]
     DoneEntry *done;         // [2G]
     int32_t *done_count;     // [1]
@@ -129,6 +149,17 @@ struct PoolDev {
     int32_t game_base;       // global index of this group's game 0 (RNG streams are keyed by the global game index)
     uint32_t rec_cap_words;
     uint64_t seed;
+    // speculative evaluation (search pools; all null / 0 otherwise)
+    CacheTag *cache_tag;     // [G][cache_entries]
+    double *cache_exps;      // [G * cache_entries + 1][833]  softmax numerators of a cached evaluation (last entry: trash)
+    double *cache_tot;       // [G * cache_entries + 1]       their sequential sum
+    float *cache_val;        // [G * cache_entries + 1]       value head
+    int32_t *req_out;        // [req_cap] cache entry (global index) every request of this tick is evaluated into
+    int32_t cache_entries;   // per game, a power of two >= kCacheWays
+    int32_t spec_k;          // children requested per consumed node
+    int32_t req_cap;         // requests the net kernel serves per tick
+    uint32_t tick_id;        // increments with every tick
+    int32_t favourite;       // 1: prefetch the favourite child of every node on the way down (AZ_TREE_FAVOURITE=0 switches it off)
     int32_t force_slow;      // test knob (AZ_TREE_FORCE_SLOW=1): resolve every candidate by the full scan
     unsigned long long *prof;   // AZ_POOL_PROFILE=1: [G][8] clock cycles per phase of the last tick (debug aid, normally nullptr)
 };

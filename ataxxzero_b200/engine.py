@@ -229,13 +229,17 @@ class MCTS:
     """engine.py:320-447 on a device-resident tree (one game of a ``search.Pool``)."""
     exploration_parameter = 1.0
     NODE_CAPACITY = 1 << 17           # tree slots kept on the GPU (9 KB each)
+    SPECULATE = 4                     # children evaluated ahead per consumed node (0: one leaf per net round trip)
 
     def __init__(self, root_board, use_dirichlet_noise=False, visits=None):
         assert initialized, "call engine.initialize_model(path) first"
         self.use_dirichlet_noise = use_dirichlet_noise
         self.board = root_board.copy()
+        # speculate: the device twin of NNEvaluator.add_to_queue (engine.py:166-175,387-392) -- likely children of every new
+        # node are evaluated in the same batch and linked from a cache when the search reaches them
         self.pool = search.Pool(context, 1, visits or 1, eval_mode=eval_mode, noise=use_dirichlet_noise, auto_play=False,
-                                node_capacity=self.NODE_CAPACITY, steps_per_tick=64)
+                                node_capacity=self.NODE_CAPACITY, steps_per_tick=64,
+                                speculate=self.SPECULATE if eval_mode != search.EVAL_FP32 else 0)
         self.pool.set_root(0, self.board.to_position())
         self._target = 0
         self._snapshot = None

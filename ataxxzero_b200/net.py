@@ -12,6 +12,7 @@ from .model import Network
 
 FP32 = 0     # AZ_NET_FP32: CUDA-core fp32, reference-accurate
 BF16 = 1     # AZ_NET_BF16: tcgen05 tensor cores, fp32 accumulate
+F16 = 3      # AZ_NET_F16: the same kernel with IEEE-half operands (3 more mantissa bits)
 
 _vp = C.c_void_p
 _native.register("az_net_load", C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int])

@@ -13,13 +13,15 @@ from .rules import pack_move, unpack_move
 
 EVAL_FP32 = 0
 EVAL_BF16 = 1
+EVAL_F16 = 3
 EVAL_EXTERNAL = 2
 
 
 class PoolConfig(C.Structure):
     _fields_ = [("games", C.c_int32), ("visits", C.c_int32), ("max_plies", C.c_int32), ("noise", C.c_int32),
                 ("auto_play", C.c_int32), ("eval_mode", C.c_int32), ("node_capacity", C.c_int32),
-                ("steps_per_tick", C.c_int32), ("seed", C.c_uint64), ("start_fen", C.c_char * 64)]
+                ("steps_per_tick", C.c_int32), ("seed", C.c_uint64), ("start_fen", C.c_char * 64),
+                ("speculate", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class PoolStats(C.Structure):
@@ -27,7 +29,7 @@ class PoolStats(C.Structure):
                 ("positions", C.c_uint64), ("games_finished", C.c_uint64), ("games_skipped", C.c_uint64),
                 ("max_depth", C.c_uint64), ("kernel_launches", C.c_uint64), ("record_bytes", C.c_uint64),
                 ("net_seconds", C.c_double),
-                ("tree_seconds", C.c_double)]
+                ("tree_seconds", C.c_double), ("levels", C.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -57,13 +59,14 @@ class Pool:
     ``auto_play=True``: self-play generation (sample ~ visits, record, re-root, restart)."""
 
     def __init__(self, ctx, games, visits, eval_mode=EVAL_BF16, noise=False, auto_play=False, max_plies=400, seed=0,
-                 start_fen="", node_capacity=0, steps_per_tick=0):
+                 start_fen="", node_capacity=0, steps_per_tick=0, speculate=0):
         self.ctx = ctx
         cfg = PoolConfig()
         cfg.games, cfg.visits, cfg.max_plies = int(games), int(visits), int(max_plies)
         cfg.noise, cfg.auto_play, cfg.eval_mode = int(bool(noise)), int(bool(auto_play)), int(eval_mode)
         cfg.node_capacity, cfg.steps_per_tick, cfg.seed = int(node_capacity), int(steps_per_tick), int(seed) & (2**64 - 1)
         cfg.start_fen = start_fen.encode()
+        cfg.speculate = int(speculate)
         self.cfg = cfg
         self.games = int(games)
         self._h = _vp()

@@ -36,6 +36,8 @@ GAMES_PER_GPU = 2048
 VISITS = 800
 TICKS_PER_STEP = 1024
 FLOP_PER_EVAL = 347.49e6          # dense FLOPs of one forward pass
+TREE_BYTES_PER_STEP = 13000.0     # algorithmic bytes of one MCTS step (select + backup + expand)
+PERFT_OPS_PER_LEAF = 8.0          # ~4 64-bit = ~8 int32 ALU operations per counted leaf at depth >= 6
 
 
 def peaks():
@@ -118,6 +120,8 @@ class ReferencePipeline:
         self.net = net_torch.TorchNet(conv, bn)            # fp32 torch-CPU (oneDNN) stand-in for TF's sess.run
         self.ocpu = ocpu
         self.evals_per_position = None
+        self.epp_sample = ""
+        self.out = None
         if self.kind == "reference":
             self.dll = ctypes.CDLL(ocpu.REF_CLIENT_SO)
             self.dll.get_workload.restype = ctypes.c_int
@@ -134,22 +138,40 @@ class ReferencePipeline:
                                     ctypes.c_int(2 * buffer_size))
 
     def measure_evals_per_position(self):
-        """Average evaluations the REFERENCE's own search core needs per played move at this visit count
-        (tree reuse carries visits over): a short greedy game through oracle/_ref/libref.so."""
+        """Evaluations the REFERENCE's own search core needs per played move at this visit count (tree reuse carries
+        visits over, adjudicated leaves need none): counted over ONE FULL GAME -- every ply from the opening to the
+        end -- played by oracle/_ref/libref.so (reference lines 1-582 compiled here)."""
         if self.evals_per_position is None:
             if self.ocpu.Reference.available():
                 ref, orc = self.ocpu.Reference(), self.ocpu.Oracle()
-                plies, _, evals = ref.selfplay_greedy(self.ocpu.START_FEN, self.visits, 12, orc.probe_eval_ptr)
+                plies, _, evals = ref.selfplay_greedy(self.ocpu.START_FEN, self.visits, 400, orc.probe_eval_ptr)
                 self.evals_per_position = evals / max(len(plies), 1)
+                self.epp_sample = "%d evaluations over the %d plies of one full reference game" % (evals, len(plies))
             else:
                 orc = self.ocpu.Oracle()
                 tree = orc.tree(orc.set_board(self.ocpu.START_FEN), "probe")
-                for _ in range(12):
+                n = 0
+                while n < 400 and orc.result(tree.root_position()) == 0:
                     tree.search(self.visits)
                     d = tree.dist()
                     tree.play(max(d, key=lambda e: e[1])[0])
-                self.evals_per_position = tree.evals / 12.0
+                    n += 1
+                self.evals_per_position = tree.evals / max(n, 1)
+                self.epp_sample = "%d evaluations over the %d plies of one full game of the oracle port" % (tree.evals, n)
         return self.evals_per_position
+
+    def count_finished(self):
+        """(games, plies) the client has appended to its output file so far"""
+        games = plies = 0
+        try:
+            with open(self.out) as f:
+                for ln in f:
+                    if ln.strip():
+                        games += 1
+                        plies += len(json.loads(ln)["moves"])
+        except (OSError, ValueError):
+            pass
+        return games, plies
 
     def run(self, seconds, evaluator=None):
         """Returns evaluations completed in ~`seconds` of wall time.  `evaluator(features) -> (policy, value)` replaces
@@ -191,6 +213,25 @@ class ReferencePipeline:
                 pass
 
 
+def counted_variant(visits, seconds, evaluator, buffer_size=8):
+    """The reference client with few enough worker threads (2 x buffer_size) that whole games FINISH inside the sample:
+    positions are then counted from its own output file (len(moves) of every line) instead of derived from evaluations.
+    In-flight games at the end of the window are lost, so this is a lower bound that cross-checks the derived figure."""
+    pipe = ReferencePipeline(visits, buffer_size)
+    try:
+        if pipe.kind != "reference":
+            return None
+        t0 = time.perf_counter()
+        evals, _ = pipe.run(seconds, evaluator=evaluator)
+        dt = time.perf_counter() - t0
+        games, plies = pipe.count_finished()
+    finally:
+        pipe.close()
+    return {"threads": 2 * buffer_size, "seconds": dt, "games_finished": games, "positions_counted": plies,
+            "positions_per_s_counted": plies / dt, "leaf_evals_per_s": evals / dt,
+            "evals_per_counted_position": (evals / plies) if plies else None}
+
+
 def reference_sample(seconds, visits=VISITS, gpu_evaluator=None):
     pipe = ReferencePipeline(visits)
     variants = {}
@@ -209,12 +250,26 @@ def reference_sample(seconds, visits=VISITS, gpu_evaluator=None):
                 variants["reference_client_with_our_gpu_net"] = {"leaf_evals_per_s": e1 / t1, "positions_per_s": e1 / t1 / epp}
     finally:
         pipe.close()
+    if pipe.kind == "reference" and gpu_evaluator is not None:
+        # in a fresh process: the reference client keeps fill levels / the current buffer in globals that shutdown() does not
+        # reset (self_play_client.cpp:597-598,740-749), so a second launch with another buffer size trips its own assert
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "counted", "--visits", str(visits)],
+                                 capture_output=True, text=True, timeout=120)
+            variants["reference_client_with_our_gpu_net_counted"] = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as exc:
+            variants["reference_client_with_our_gpu_net_counted"] = {"error": repr(exc)}
     cores = os.cpu_count() or 1
     return {"value": evals / dt / epp, "unit": UNIT, "cores": cores, "kind": pipe.kind, "variants": variants,
+            "evals_per_position": epp, "evals_per_position_sample": pipe.epp_sample,
+            "positions_note": "a reference game needs ~%.0f evaluations per ply x ~185 plies: with 256 concurrent games none finishes "
+                              "inside a bounded sample, so positions/s = leaf-evals/s / (evaluations per ply counted over one full "
+                              "reference game); the *_counted variant runs 16 worker threads so that games do finish and counts "
+                              "len(moves) from the client's output file" % epp,
             "sample": "%.0f s of %s + torch-CPU fp32 net (TensorFlow absent), %d-visit searches, buffer 128 / 256 threads: "
-                      "%.0f leaf-evals/s / %.0f evals per played move (measured on the reference search core)"
+                      "%.0f leaf-evals/s / %.0f evals per played move (%s)"
                       % (dt, "oracle/_ref/self_play_client.so" if pipe.kind == "reference" else "oracle C port", visits,
-                         evals / dt, epp)}
+                         evals / dt, epp, pipe.epp_sample)}
 
 
 def run_reference(args):
@@ -242,7 +297,9 @@ def run_reference(args):
             "config": {"workload": "selfplay %d-visit MCTS, reference CPU pipeline (buffer 128 / 256 threads)" % VISITS,
                        "visits": VISITS, "buffer_size": 128, "step": "%.1f s sample" % step_s},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": pipe.kind,
-                             "sample": "%d x %.1f s; %.0f leaf-evals/s / %.0f evals per played move" % (k, step_s, evals / dt, epp)},
+                             "sample": "%d x %.1f s; %.0f leaf-evals/s / %.0f evals per played move (%s)" % (k, step_s, evals / dt, epp, pipe.epp_sample)},
+            "positions_note": "no reference game finishes inside the sample (%.0f evaluations per ply x ~185 plies x 256 concurrent "
+                              "games): positions = leaf evaluations / evaluations per ply, counted over one full reference game" % epp,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -369,7 +426,25 @@ def run_ours(args):
                 "peak_kind": "%s bf16_tflops_sustained (kernel timed inside a long step)" % pk_kind,
                 "net_share_of_step": d["net_seconds"] / max(d["net_seconds"] + d["tree_seconds"], 1e-9),
                 "tree_ms_per_tick": d["tree_seconds"] / max(d["ticks"], 1) * 1e3,
-                "net_ms_per_tick": d["net_seconds"] / max(d["ticks"], 1) * 1e3}
+                "net_ms_per_tick": d["net_seconds"] / max(d["ticks"], 1) * 1e3,
+                "timing": "CUDA events around EVERY k_tree_tick and k_net_tc launch of the timed region (summed, not sampled)"}
+    # tree kernel: HBM roofline on SURVEY 8(d)'s algorithmic bytes of the reference algorithm (13 KB per MCTS step: every
+    # child's P/W/n at every level of the selection path, the backup, 833 logits, the new node)
+    tree_s = max(d["tree_seconds"], 1e-9)
+    tree_bytes = d["steps"] * TREE_BYTES_PER_STEP
+    hbm_peak = float(pk.get("hbm_gbs", 6550.0))
+    try:
+        tree_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_tree_tick"]["dram_bytes_per_launch"]
+    except Exception:
+        tree_traffic = None
+    roofline["kernels"] = {
+        "k_tree_tick": {"bound": "hbm", "achieved": tree_bytes / tree_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": tree_bytes / tree_s / 1e9 / hbm_peak, "traffic": tree_traffic,
+                        "algorithmic_bytes_per_step": TREE_BYTES_PER_STEP, "steps_per_launch": d["steps"] / max(d["ticks"], 1),
+                        "levels_per_step": d.get("levels", 0) / max(d["steps"], 1),
+                        "us_per_level_per_game": tree_s * 1e6 / max(d["ticks"], 1) / max(d.get("levels", 0) / max(d["ticks"], 1) / games, 1e-9),
+                        "note": "latency-bound by design: one warp per game walks a dependent chain of tree levels; the compact node "
+                                "layout reads far fewer bytes than the reference algorithm's 13 KB per step"}}
 
     # ---- end to end: host weights in, JSON game records out, every step ----
     out_path = azdist.rank_output_path(os.path.join(tempfile.gettempdir(), "az_bench_model-001.json"), rank, max(world, 2))
@@ -389,6 +464,7 @@ def run_ours(args):
     e1 = pool.stats()
     barrier()
     e2e_positions = allreduce(e1["positions"] - e0["positions"])
+    e2e_evals = allreduce(e1["evals"] - e0["evals"])
     record_bytes = e1["record_bytes"] - e0["record_bytes"]
     try:
         json_bytes = os.path.getsize(out_path)
@@ -397,6 +473,7 @@ def run_ours(args):
         json_bytes = 0
     e2e = {"value": e2e_positions / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(packed.nbytes),
            "d2h_bytes_per_step": int(record_bytes / k), "json_bytes_per_step": int(json_bytes / k),
+           "leaf_evals_per_s": e2e_evals / e2e_s,
            "api": "net.load_packed (pinned host weights) + Pool.selfplay_ticks(ticks, path) -> az_net_load / az_selfplay_ticks"}
 
     # ---- BASELINE configs[4]: single-tree search (replicas only, rank 0) + leaf-batch latency of the net kernel ----
@@ -404,28 +481,70 @@ def run_ours(args):
     if rank == 0 and not args.no_single_tree:
         golden = os.path.join(ROOT, "tests", "golden", "mcts_golden.json")
         fen = json.load(open(golden))["midgame_fen"] if os.path.exists(golden) else rules.START_FEN
-        with search.Pool(ctx, 1, 64, eval_mode=search.EVAL_BF16, node_capacity=args.single_tree_visits + 64, steps_per_tick=64) as tree:
-            tree.set_root(0, rules.set_board(fen))
-            tree.run()                                   # warm-up: 64 visits
-            tree.set_visits(args.single_tree_visits)
-            t0 = time.perf_counter()
-            tree.run()
-            dt = time.perf_counter() - t0
-            st = tree.stats()
-            single = {"fen": fen, "visits": args.single_tree_visits, "visits_per_s": (args.single_tree_visits - 64) / dt,
-                      "mode": "bit-exact sequential PUCT (one leaf per tick, no virtual loss)", "ticks": st["ticks"]}
+        single = {"fen": fen, "visits": args.single_tree_visits, "runs": {}}
+        root_ref = None
+        for spec in (0, 4, 16):       # 0 = one leaf per net round trip; k = the k likeliest children of every new node ride along
+            with search.Pool(ctx, 1, 64, eval_mode=search.EVAL_BF16, node_capacity=args.single_tree_visits + 64, steps_per_tick=64,
+                             speculate=spec) as tree:
+                tree.set_root(0, rules.set_board(fen))
+                tree.run()                                   # warm-up: 64 visits
+                tree.set_visits(args.single_tree_visits)
+                st0 = tree.stats()
+                t0 = time.perf_counter()
+                tree.run()
+                dt = time.perf_counter() - t0
+                st = tree.stats()
+                root = tree.root(0)
+                if root_ref is None:
+                    root_ref = root
+                same = root["visits"] == root_ref["visits"] and [float(x).hex() for x in root["total_score"]] == [float(x).hex() for x in root_ref["total_score"]]
+                single["runs"]["speculate_%d" % spec] = {
+                    "visits_per_s": (args.single_tree_visits - 64) / dt, "ticks": st["ticks"] - st0["ticks"],
+                    "visits_per_tick": (args.single_tree_visits - 64) / max(st["ticks"] - st0["ticks"], 1),
+                    "us_per_tick": dt * 1e6 / max(st["ticks"] - st0["ticks"], 1),
+                    "root_identical_to_one_leaf_per_tick": bool(same)}
+        best = max(single["runs"].values(), key=lambda r: r["visits_per_s"])
+        single["visits_per_s"] = best["visits_per_s"]
+        single["mode"] = ("bit-exact sequential PUCT, no virtual loss; speculate_k: the k highest-prior children of every consumed node are "
+                          "evaluated in the same batch and linked from a per-tree cache when the search reaches them (engine.py:387-392)")
         lat = {}
         feats = np.zeros((128, 7, 7, 4), dtype=np.float32)
         feats[..., 0] = 1.0
         for b in (1, 8, 32, 128):
             samples = []
-            for _ in range(30):
+            for _ in range(200):
                 t0 = time.perf_counter()
                 net.forward(ctx, feats[:b], net.BF16)
                 samples.append((time.perf_counter() - t0) * 1e6)
             samples.sort()
-            lat["batch%d" % b] = {"p50_us": samples[len(samples) // 2], "p99_us": samples[-1]}
+            lat["batch%d" % b] = {"p50_us": samples[len(samples) // 2], "p99_us": samples[int(0.99 * len(samples))]}
         single["leaf_batch_latency_host_to_host"] = lat
+
+    # ---- BASELINE configs[2]: 256 concurrent games x 400 visits on one B200 (>= 10 k recorded positions after warm-up) ----
+    config3 = {}
+    if rank == 0 and not args.no_single_tree:
+        with search.Pool(ctx, 256, 400, eval_mode=search.EVAL_BF16, noise=True, auto_play=True, seed=3000) as small:
+            small.set_roots(synthetic_roots(ctx, 256, seed=77))
+            small.selfplay_ticks(2048)                   # warm-up
+            c0 = small.stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ctx.sync()
+            e0.record(stream)
+            done = 0
+            while done < 64 * 1024:
+                small.selfplay_ticks(4096)
+                done += 4096
+                if small.stats()["positions"] - c0["positions"] >= 10000:
+                    break
+            e1.record(stream)
+            ctx.sync()
+            c1 = small.stats()
+            cms = e0.elapsed_time(e1)
+            cd = {key: c1[key] - c0[key] for key in c1}
+            config3 = {"games": 256, "visits": 400, "positions": cd["positions"], "positions_per_s": cd["positions"] / (cms * 1e-3),
+                       "leaf_evals_per_s": cd["evals"] / (cms * 1e-3), "ms_per_tick": cms / max(cd["ticks"], 1),
+                       "tree_ms_per_tick": cd["tree_seconds"] / max(cd["ticks"], 1) * 1e3,
+                       "net_ms_per_tick": cd["net_seconds"] / max(cd["ticks"], 1) * 1e3}
 
     # ---- BASELINE configs[0]: uniformly random play, 2000 games, on the device (records copied back to the host) ----
     start = rules.set_board(rules.OPEN_FEN)
@@ -443,8 +562,16 @@ def run_ours(args):
         nodes = rules.perft(ctx, p, depth)
         dt = time.perf_counter() - t0
         perft["depth%d" % depth] = {"nodes": nodes, "mnodes_per_s": nodes / dt / 1e6}
-    try:        # integer-ALU roofline of the perft walk kernel, from the committed ncu capture (profiles/)
-        perft["k_walk_alu_pipe_pct_of_peak_ncu"] = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_walk"]["alu_pipe_pct_of_peak_active"]
+    try:        # integer-ALU roofline of the perft walk kernel: algorithmic int32 ops per leaf x leaves/s against the measured
+        # issue peak of the integer pipe (tools/micro/int_alu_peak.cu, same pool), plus the ncu pipe utilisation (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        perft["k_walk_alu_pipe_pct_of_peak_ncu"] = tj["k_walk"]["alu_pipe_pct_of_peak_active"]
+        int_peak = float(tj["int_alu_peak"]["iadd3_tops"])
+        ach = perft["depth8"]["mnodes_per_s"] * 1e6 * PERFT_OPS_PER_LEAF / 1e12
+        roofline["kernels"]["k_walk (perft depth 8)"] = {
+            "bound": "int_alu", "achieved": ach, "peak": int_peak, "unit": "Tops/s (int32)", "frac": ach / int_peak,
+            "ops_per_leaf": PERFT_OPS_PER_LEAF, "traffic": tj["k_walk"].get("dram_bytes_per_launch"),
+            "note": "ops per leaf is SURVEY 8(d)'s algorithmic estimate; peak = measured IADD3 issue rate; wall clock incl. frontier expansion"}
     except Exception:
         pass
 
@@ -460,7 +587,7 @@ def run_ours(args):
             "e2e": e2e, "roofline": roofline, "clocks": clocks, "gpu_launches": int(d["kernel_launches"]),
             "extra": {"leaf_evals_per_s": evals / (ms * 1e-3), "mcts_steps_per_s": steps / (ms * 1e-3),
                       "evals_per_position": evals / max(positions, 1), "max_depth": s1["max_depth"], "perft": perft,
-                      "single_tree": single, "random_play": random_play}}
+                      "single_tree": single, "config3_256x400": config3, "random_play": random_play}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pool.close()
         try:
@@ -474,6 +601,18 @@ def run_ours(args):
                 nN, sN = ocpu.ref_perft(ocpu.OPEN_FEN, 7, cores)
                 line["cpu_baseline"]["perft"] = {"kind": "reference", "depth6_1thread_mnodes_per_s": n1 / s1 / 1e6,
                                                  "depth7_%dthreads_mnodes_per_s" % cores: nN / sN / 1e6, "nodes": [n1, nN]}
+            # the honest comparisons with the reference's own SEARCH ENGINE: the unmodified client fed by our GPU
+            # net through its legacy ABI, and its host side alone with a zero-cost evaluator
+            var = line["cpu_baseline"].get("variants", {})
+            if var.get("reference_client_with_our_gpu_net"):
+                line["vs_reference_client_gpu_net"] = e2e["leaf_evals_per_s"] / var["reference_client_with_our_gpu_net"]["leaf_evals_per_s"]
+            if var.get("zero_cost_evaluator_host_ceiling"):
+                line["vs_reference_host_ceiling"] = e2e["leaf_evals_per_s"] / var["zero_cost_evaluator_host_ceiling"]["leaf_evals_per_s"]
+            line["vs_reference_note"] = ("e2e leaf evaluations/s of this arm (search + net + records, host in / host out) / leaf evaluations/s of "
+                                         "the unmodified reference client on the box's host cores: fed by OUR GPU net through its own legacy ABI, "
+                                         "and with a zero-cost evaluator (its thread pool + hash-map trees alone).  Leaf evaluations are what both "
+                                         "pipelines count exactly; positions/s = that / evaluations per ply, the same factor for the same games.  "
+                                         "The --impl reference arm additionally pays for an fp32 conv net on the host cores")
         except Exception as exc:        # the baseline is reported, never the product path
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable",
                                     "sample": "failed: %r" % (exc,)}
@@ -488,16 +627,23 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "counted"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
     ap.add_argument("--visits", type=int, default=VISITS)
     ap.add_argument("--ticks-per-step", type=int, default=TICKS_PER_STEP)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single-tree", action="store_true")
-    ap.add_argument("--single-tree-visits", type=int, default=4000)
+    ap.add_argument("--single-tree-visits", type=int, default=100000)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "counted":         # helper of the cpu_baseline leg (see reference_sample)
+        import ataxxzero_b200 as az
+        from ataxxzero_b200 import model, net
+        ctx = az.Context(device=0, seed=1)
+        net.load_weights(ctx, model.Network.random_init(seed=0))
+        res = counted_variant(args.visits, 12.0, lambda f: net.forward(ctx, f, net.BF16))
+        print(json.dumps(res), flush=True)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

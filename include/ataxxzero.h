@@ -103,7 +103,10 @@ int az_random_playouts(az_context *ctx, const az_position *start, int n_games, i
 /* ---------------- network (model.py:38-79 forward; .npy weights model.py:179-196) ------------- */
 /* Precision modes of the forward pass. */
 #define AZ_NET_FP32   0   /* CUDA-core fp32, reference-accurate (<= 1e-5 vs the fp32/fp64 restatement) */
-#define AZ_NET_BF16   1   /* bf16 tcgen05 tensor-core implicit GEMM, fp32 accumulate (<= 2e-2 abs)      */
+#define AZ_NET_BF16   1   /* bf16 tcgen05 tensor-core implicit GEMM, fp32 accumulate (<= 2e-2 abs at the scale of the
+                             reference's initialisation; 8-bit mantissa: ~1.4 % rms of the logit scale for a trained net) */
+#define AZ_NET_F16    3   /* the same kernel with IEEE-half operands (11-bit mantissa, same tensor throughput): <= 2e-2 abs
+                             also for trained-scale logits; operands must stay below 65504 (batch-normalised towers do)  */
 
 /* Upload weights.  `packed` is float32, host memory, in model.py parameter order:
  *   W_in[3][3][4][F], then 2*blocks x W[3][3][F][F]   (TF layout [kh(x)][kw(y)][Cin][Cout]),
@@ -146,6 +149,11 @@ typedef struct {
     int32_t steps_per_tick; /* max MCTS steps a game may take per tick without needing the net; 0 = 8       */
     uint64_t seed;          /* Philox stream for move sampling and Dirichlet noise                           */
     char start_fen[64];     /* "" = STARTING_GAME_POSITION (self_play_client.cpp:23)                         */
+    int32_t speculate;      /* search pools (auto_play = 0) on the tensor-core net: every time a node's evaluation is consumed,
+                               the evaluations of its `speculate` highest-prior children are requested in the same batch and
+                               kept in a per-game cache (engine.py:387-392 queues likely children the same way); a leaf whose
+                               position is cached links without waiting for the net.  Visit counts are unchanged.  0 = off */
+    int32_t reserved[3];
 } az_pool_config;
 
 typedef struct {
@@ -159,8 +167,9 @@ typedef struct {
     uint64_t max_depth;        /* deepest selection path seen                                     */
     uint64_t kernel_launches;  /* kernels launched by the pool                                    */
     uint64_t record_bytes;     /* game-record bytes copied device -> host                         */
-    double   net_seconds;      /* device time in the net kernel (CUDA events; 0 if not measured)  */
+    double   net_seconds;      /* device time in the net kernel (CUDA events around every launch)  */
     double   tree_seconds;     /* device time in the tree kernel                                  */
+    uint64_t levels;           /* tree levels walked by completed selections (sum of path lengths) */
 } az_pool_stats;
 
 int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_pool **out);

@@ -97,6 +97,9 @@ void ao_set_prior_perturbation(int mode);
 
 /* ---- tree_model.c: CPU model of the device tree algorithm (candidate + visited list), checked against ao_mcts ---- */
 long tm_selftest(const char *fen, int visits, int evaluator, int plays, int force_slow, long *counters_out);
+/* net round trips a bit-exact single-tree search needs when the top_k children of every consumed node are evaluated
+ * speculatively (evaluator 2: nearly uniform priors, values ~0, like the benchmark's random-init net) */
+long tm_spec_sim(const char *fen, int visits, int evaluator, int top_k, long *evals_out);
 
 /* convenience: search `visits` from fen with a named evaluator (0 probe, 1 uniform),
  * fill root distribution; returns n_moves or <0 on error. */

@@ -68,6 +68,35 @@ def randomize_bn(bn, seed=1):
     return out
 
 
+def trained_scale_weights(seed=0, logit_std=2.0, value_std=1.5, batch=64):
+    """Random weights with the STATISTICS of a trained network (the reference ships none): every batch-norm layer's moving
+    mean / variance are set to the actual per-channel moments of its input on a calibration batch, so each layer emits
+    unit-variance channels the way a trained tower does (instead of the 0.2-gain init, whose activations stay tiny), the
+    policy head is scaled until the logits have standard deviation `logit_std` (|logit| up to ~4 sigma) and the value head
+    until tanh saturates for part of the batch.  Returns (conv, bn) as float32 lists like init_weights()."""
+    conv, bn = init_weights(seed)
+    conv = [np.asarray(a, dtype=np.float64) for a in conv]
+    bn = [np.asarray(a, dtype=np.float64) for a in bn]
+    blocks = (len(conv) - 5) // 2
+    x = random_features(batch, seed=seed + 100).astype(np.float64)
+
+    def calibrate(v, k):
+        y = _conv_same(v, conv[k])
+        bn[2 * k] = y.mean(axis=(0, 1, 2))
+        bn[2 * k + 1] = y.var(axis=(0, 1, 2)) + 1e-6
+        return (y - bn[2 * k]) / np.sqrt(bn[2 * k + 1] + BN_EPS)
+
+    x = np.maximum(calibrate(x, 0), 0)
+    for b in range(blocks):
+        skip = x
+        x = np.maximum(calibrate(x, 1 + 2 * b), 0)
+        x = np.maximum(calibrate(x, 2 + 2 * b) + skip, 0)
+    conv[-4] = conv[-4] * (logit_std / _conv_same(x, conv[-4]).std())
+    v = _conv_same(x, conv[-3]).reshape(batch, BOARD * BOARD) @ conv[-2]
+    conv[-3] = conv[-3] * (value_std / v.std())
+    return [a.astype(np.float32) for a in conv], [a.astype(np.float32) for a in bn]
+
+
 def save_model(path, conv, bn):
     """model.py:179-183 -- ``np.save(path, [conv_weights, bn_params])`` (2-element object array)."""
     box = np.empty(2, dtype=object)

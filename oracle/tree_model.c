@@ -346,3 +346,68 @@ long tm_selftest(const char *fen, int visits, int evaluator, int plays, int forc
     tm_free(t);
     return bad;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Tick simulation of SPECULATIVE leaf evaluation for single-tree search (BASELINE config 5): how many net round trips
+ * ("ticks") does a bit-exact sequential search need when, each time a node's evaluation is consumed, the evaluations of
+ * its `top_k` highest-prior children are requested in the same batch (engine.py:387-392 queues children with prior > 0.15
+ * the same way)?  A child that was requested in an EARLIER tick links without waiting; everything else costs a tick.
+ * Evaluator 2 mimics the random-init net of the benchmark: nearly uniform priors, values within +-0.005.
+ * Returns the number of ticks; *evals_out = evaluations requested (speculative ones included).
+ * ------------------------------------------------------------------------------------------------ */
+static void flat_eval(void *ctx, const float feats[AO_FEATURES], float logits[AO_LOGITS], float *value)
+{
+    ao_probe_eval(ctx, feats, logits, value);
+    for (int i = 0; i < AO_LOGITS; i++) logits[i] *= 0.025f;       /* logit std ~0.03 like model-001 */
+    *value *= 0.006f;
+}
+
+long tm_spec_sim(const char *fen, int visits, int evaluator, int top_k, long *evals_out)
+{
+    ao_position p;
+    if (ao_set_board(&p, fen) != 0) return -1;
+    ao_eval_fn fn = evaluator == 1 ? ao_uniform_eval : evaluator == 2 ? flat_eval : ao_probe_eval;
+    tm_tree *t = (tm_tree *)tm_new(&p, fn, NULL, 0);
+    long now = 1, requested = 1;       /* the root evaluation: requested in tick 0, ready in tick 1 */
+    /* per node: the tick in which its evaluation was CONSUMED (side table in order of creation; recent nodes are found first) */
+    typedef struct { tm_node *n; long consumed; } rec;
+    rec *recs = (rec *)calloc((size_t)visits + 8, sizeof(rec));
+    long n_recs = 0;
+    recs[n_recs].n = t->root; recs[n_recs].consumed = 1; n_recs++;
+    while (t->root->N < visits) {
+        /* one step, with timing: find the parent of the node this step will expand */
+        tm_node *node = t->root;
+        int sel;
+        for (;;) {
+            sel = tm_select(t, node);
+            if (sel < 0 || sel <= -2) break;
+            node = node->ent[sel].child;
+        }
+        if (sel <= -2) {
+            const int idx = -2 - sel;
+            /* parent's consumption tick */
+            long consumed = 0;
+            for (long i = n_recs - 1; i >= 0; i--) if (recs[i].n == node) { consumed = recs[i].consumed; break; }
+            /* was this child among the parent's top_k priors? */
+            int better = 0;
+            for (int i = 0; i < node->L; i++) if (node->P[i] > node->P[idx]) better++;
+            long ready;
+            if (better < top_k) ready = consumed + 1;            /* requested when the parent was consumed */
+            else { ready = now + 1; requested++; }               /* requested only now */
+            if (ready > now) now = ready;
+            tm_step(t);
+            tm_node *leaf = node->ent[node->k - 1].child;
+            if (!leaf->terminal) {
+                recs[n_recs].n = leaf; recs[n_recs].consumed = now; n_recs++;
+                int spec = leaf->L < top_k ? leaf->L : top_k;
+                requested += spec;
+            }
+        } else {
+            tm_step(t);                                          /* terminal re-visit: no evaluation */
+        }
+    }
+    if (evals_out) *evals_out = requested;
+    free(recs);
+    tm_free(t);
+    return now;
+}

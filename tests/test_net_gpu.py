@@ -97,6 +97,66 @@ def test_bf16_mode_within_tolerance(ctx, nets):
     assert np.abs(got_v - want_v).max() < BF16_TOL
 
 
+def test_bf16_at_trained_scale(ctx, nets):
+    """Calibrated batch-norm statistics, logits of standard deviation 2 (|logit| up to ~9), saturating values: the regime
+    of a TRAINED net, where the random-init tests above are loose.  An 8-bit mantissa cannot hold north_star's 2e-2
+    absolute on logits of magnitude 9: every operand is rounded to 2^-9 relative, ~50 roundings deep, and the measured
+    error is what that predicts -- 1.4 % rms of the logit scale, growing as sqrt(depth) (profiles/r02_net_error.txt, per
+    layer).  So at this scale the bf16 bound is RELATIVE (the absolute 2e-2 is kept for logits of the benchmark's scale,
+    test_bf16_mode_within_tolerance); the fp16-operand mode (test_f16_mode_keeps_2e2_at_trained_scale) keeps 2e-2
+    absolute here, and the fp32 mode keeps 1e-5 of full scale (float32 itself is 1e-5 from fp64 at this magnitude)."""
+    from ataxxzero_b200 import model, net
+    from oracle import net_numpy
+    conv, bn = net_numpy.trained_scale_weights(seed=0, logit_std=2.0)
+    net.load_weights(ctx, model.Network(conv, bn))
+    try:
+        feats = _features(24, 21)
+        want_p, want_v = net_numpy.forward(feats, conv, bn, dtype=np.float64)
+        full = np.abs(want_p).max()
+        assert full > 5.0 and np.abs(want_v).max() > 0.99            # the regime the test is about
+        got_p, got_v = net.forward(ctx, feats, net.BF16)
+        err = np.abs(got_p - want_p)
+        assert err.max() < 0.03 * full                                # measured 1.5 %
+        assert np.sqrt((err ** 2).mean()) < 0.025 * want_p.std()      # measured 1.4 %
+        assert np.abs(got_v - want_v).max() < 0.15                    # measured 0.08 (where tanh is steep)
+        # the priors the search actually consumes: softmax over the legal-move-sized logit vector moves by a few percent
+        sm = lambda z: np.exp(z - z.max(axis=(1, 2, 3), keepdims=True)) / np.exp(z - z.max(axis=(1, 2, 3), keepdims=True)).sum(axis=(1, 2, 3), keepdims=True)
+        assert np.abs(sm(got_p.astype(np.float64)) - sm(want_p)).max() < 0.02
+        p32, v32 = net.forward(ctx, feats, net.FP32)
+        assert np.abs(p32 - want_p).max() < FP32_TOL * max(full, 1.0) and np.abs(v32 - want_v).max() < 5 * FP32_TOL
+    finally:
+        net.load_weights(ctx, nets)
+
+
+def test_f16_mode_keeps_2e2_at_trained_scale(ctx, nets):
+    """AZ_NET_F16: same tcgen05 kernel, IEEE-half operands (11-bit mantissa).  north_star's 2e-2 absolute holds for
+    trained-scale logits (|logit| up to ~9) and saturating values, and at the benchmark's scale the error drops ~8x."""
+    from ataxxzero_b200 import model, net
+    from oracle import net_numpy
+    conv, bn = net_numpy.trained_scale_weights(seed=0, logit_std=2.0)
+    net.load_weights(ctx, model.Network(conv, bn))
+    try:
+        feats = _features(24, 21)
+        want_p, want_v = net_numpy.forward(feats, conv, bn, dtype=np.float64)
+        got_p, got_v = net.forward(ctx, feats, net.F16)
+        assert np.isfinite(got_p).all() and np.isfinite(got_v).all()
+        assert np.abs(got_p - want_p).max() < BF16_TOL
+        assert np.abs(got_v - want_v).max() < BF16_TOL
+        bp, _ = net.forward(ctx, feats, net.BF16)
+        assert np.abs(got_p - want_p).max() < 0.25 * np.abs(bp - want_p).max()
+    finally:
+        net.load_weights(ctx, nets)
+    feats = _features(64, 23)
+    want_p, want_v = net_numpy.forward(feats, nets.conv, nets.bn, dtype=np.float64)
+    got_p, got_v = net.forward(ctx, feats, net.F16)
+    assert np.abs(got_p - want_p).max() < 3e-4 and np.abs(got_v - want_v).max() < 3e-4
+    # and a search pool can run on it
+    from ataxxzero_b200 import rules, search
+    with search.Pool(ctx, 2, 40, eval_mode=search.EVAL_F16) as pool:
+        pool.run()
+        assert pool.root(0)["root_visits"] >= 40
+
+
 def test_modes_agree_and_batch_invariance(ctx, nets):
     from ataxxzero_b200 import net
     feats = _features(64, 9)

@@ -304,3 +304,21 @@ def test_live_reference_edge_positions(oracle, reference):
         if oracle.result(p) == 0:
             for m in mo:
                 assert oracle.makemove(p, m).key() == reference.makemove(p, m).key(), (fen, m)
+
+
+def test_net_oracle_has_three_unrelated_witnesses():
+    """The net oracle is parity-unpinned (no TensorFlow here, no reference goldens).  Three evaluations that share no
+    code path must agree on it: NumPy shifted-window matmuls (the oracle), torch/oneDNN conv2d, and scipy's direct
+    cross-correlation on an explicitly padded board with a hand-written value head (oracle/net_scipy.py) -- at random-init
+    scale and at trained scale (calibrated batch-norm, large logits, saturating values)."""
+    from oracle import net_numpy, net_scipy, net_torch
+    cases = [net_numpy.init_weights(seed=3), net_numpy.trained_scale_weights(seed=1)]
+    cases[0] = (cases[0][0], net_numpy.randomize_bn(cases[0][1], seed=2))
+    for conv, bn in cases:
+        feats = net_numpy.random_features(2, seed=17)
+        want_p, want_v = net_numpy.forward(feats, conv, bn, dtype=np.float64)
+        scale = max(1.0, float(np.abs(want_p).max()))
+        sp, sv = net_scipy.forward_one(feats[0], conv, bn)
+        assert np.abs(sp - want_p[0]).max() < 1e-12 * scale and abs(sv - want_v[0, 0]) < 1e-12
+        tp, tv = net_torch.TorchNet(conv, bn).forward(feats)
+        assert np.abs(tp - want_p).max() < 2e-5 * scale and np.abs(tv - want_v).max() < 2e-5

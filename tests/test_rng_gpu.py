@@ -107,8 +107,11 @@ def test_selfplay_first_moves_follow_visit_table(ctx):
     first moves of many games are draws from ONE visit distribution (the one a single search tree reports)"""
     from scipy import stats
     from ataxxzero_b200 import model, net, rules, search
-    net.load_weights(ctx, model.Network.random_init(seed=0))
-    games, visits = 2048, 60
+    from oracle import net_numpy
+    # a net with trained-scale statistics: its sharper priors and varied values spread the 200 visits of the opening over
+    # several moves (the random-init net puts them all on one, FPU = 0)
+    net.load_weights(ctx, model.Network(*net_numpy.trained_scale_weights(seed=0)))
+    games, visits = 2048, 200
     os.environ["AZ_REQ_CAP"] = "0"          # serve every request every tick: the games stay in lockstep up to their first move
     try:
         pool = search.Pool(ctx, games, visits, eval_mode=search.EVAL_BF16, noise=False, auto_play=True, seed=6)
@@ -136,8 +139,8 @@ def test_selfplay_first_moves_follow_visit_table(ctx):
     live = weights > 0
     assert counts[~live].sum() == 0
     chi = stats.chisquare(counts[live], weights[live] / weights.sum() * games)
+    assert live.sum() >= 3, weights
     assert chi.pvalue > 1e-4, (chi, counts, weights)
-    assert len(set(counts[live])) > 1 or live.sum() == 1
 
 
 def test_forced_full_scan_selection_matches_goldens(ctx, oracle):

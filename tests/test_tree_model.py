@@ -64,3 +64,17 @@ def test_perturbed_priors(lib, perturb):
 def test_deep_search(lib):
     bad, counters = run(lib, MIDGAME, 20000, 0, plays=1)
     assert bad == 0, counters
+
+
+def test_speculative_evaluation_tick_model(lib):
+    """design evidence for the speculative single-tree search (csrc/az_tree.cu, cache mode): the number of net round trips
+    with the top-k children of every consumed node evaluated in the same batch, against one round trip per visit"""
+    lib.tm_spec_sim.restype = C.c_long
+    lib.tm_spec_sim.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
+    evals = C.c_long()
+    base = lib.tm_spec_sim(MIDGAME.encode(), 3000, 2, 0, C.byref(evals))
+    assert base in (3000, 3001) and evals.value == base
+    for k, least in ((1, 2.0), (16, 3.0)):
+        ticks = lib.tm_spec_sim(MIDGAME.encode(), 3000, 2, k, C.byref(evals))
+        assert 3000 / ticks > least, (k, ticks)
+        assert evals.value <= 3001 * (k + 1)
