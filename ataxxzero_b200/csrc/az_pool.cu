@@ -66,7 +66,9 @@ struct az_pool {
     int net_tiles = 0;                    // net kernel variant used by this pool (0 = context default)
     int pending_requests = 0;             // external mode: requests handed out by collect()
     uint64_t ticks = 0, launches = 0;
-    double net_seconds = 0.0, tree_seconds = 0.0;
+    double net_seconds = 0.0, tree_seconds = 0.0;     // sums over every launch of the self-play loop (CUDA events)
+    double tick_seconds = 0.0;                        // every tick, first event to last
+    uint64_t timed_ticks = 0;                         // ticks behind the three sums
     uint64_t written_games = 0, written_positions = 0, d2h_bytes = 0;
 
     Group &group_of(int game, int *local)
@@ -136,7 +138,7 @@ int launch_net(az_pool *pool, Group &grp)
                                      D.req_count + 2 * grp.slot, grp.stream, pool->net_tiles, D.cache_exps, D.cache_tot, D.req_out);
     else
         rc = az_net_forward_internal(pool->ctx, D.req_pos, AZ_IN_POS, D.cap, pool->cfg.eval_mode, D.logits, D.values,
-                                     D.req_count + 2 * grp.slot, grp.stream, pool->net_tiles, D.exps, D.totals);
+                                     D.req_count + 2 * grp.slot, grp.stream, pool->net_tiles);
     pool->launches++;
     return rc;
 }
@@ -246,7 +248,7 @@ int drain_finished(az_pool *pool, Group &grp, FILE *out, int64_t *games_written,
 void free_group(Group &grp)
 {
     PoolDev &D = grp.dev;
-    void *ptrs[] = {D.nodes, D.games, D.path, D.gstack, D.req_pos, D.req_game, D.req_count, D.logits, D.values, D.exps, D.totals, D.cache_tag,
+    void *ptrs[] = {D.nodes, D.games, D.path, D.gstack, D.req_pos, D.req_game, D.req_count, D.logits, D.values, D.cache_tag,
                     D.cache_exps, D.cache_tot, D.cache_val, D.req_out, D.records,
                     D.done, D.done_count, grp.d_done_snapshot, grp.d_status, grp.d_features, grp.d_offsets, grp.d_stage};
     for (void *p : ptrs)
@@ -378,7 +380,6 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         D.seed = cfg->seed;
         D.tick_cycles = getenv("AZ_TICK_CYCLES") ? atoi(getenv("AZ_TICK_CYCLES")) : 0;
         D.force_slow = getenv("AZ_TREE_FORCE_SLOW") ? atoi(getenv("AZ_TREE_FORCE_SLOW")) : 0;
-        D.favourite = getenv("AZ_TREE_FAVOURITE") ? atoi(getenv("AZ_TREE_FAVOURITE")) : 1;
         D.rec_cap_words = rec_cap_words;
         const size_t G = (size_t)D.G;
         rc |= dev_alloc(&D.nodes, G * D.C * kNodeStride, false);
@@ -407,9 +408,6 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
             cudaFree(D.req_pos);
             D.req_pos = nullptr;
             rc |= dev_alloc(&D.req_pos, (size_t)std::max<int>(D.req_cap, (int)G));
-        } else if (tensor_net && !getenv("AZ_TREE_SOFTMAX")) {     // the net kernel delivers the softmax front half
-            rc |= dev_alloc(&D.exps, G * AZ_LOGITS);
-            rc |= dev_alloc(&D.totals, G);
         }
         rc |= dev_alloc(&D.records, G * 2 * D.rec_cap_words, false);
         rc |= dev_alloc(&D.done, 2 * G);
@@ -519,6 +517,8 @@ extern "C" int az_pool_stats_get(az_pool *pool, az_pool_stats *out)
     s.record_bytes = pool->d2h_bytes;
     s.net_seconds = pool->net_seconds;
     s.tree_seconds = pool->tree_seconds;
+    s.tick_seconds = pool->tick_seconds;
+    s.timed_ticks = pool->timed_ticks;
     *out = s;
     return AZ_OK;
 }
@@ -789,8 +789,15 @@ namespace {
 
 // `ticks` (<= kTicksPerDrain) iterations of (tree kernel, net kernel) per group, the groups' launches interleaved on their
 // own streams, then one drain of finished games.  Every tick is bracketed by CUDA events on the launching stream; after the
-// drain's synchronisation the per-launch times are summed into tree_seconds / net_seconds (with several groups these are
-// launch-to-completion times of overlapping kernels).
+// drain's synchronisation the per-launch times are summed into tree_seconds / net_seconds / tick_seconds -- every launch is
+// measured, nothing is extrapolated (with several groups these are launch-to-completion times of overlapping kernels).
+//
+// Measured and rejected (r02, profiles/r02_early_launch_trace.txt): launching the net kernel PROGRAMMATICALLY behind the tree
+// kernel (griddepcontrol.launch_dependents + request-slot stamps) so that the tree's tail -- its slowest game takes twice as
+// long as the median one -- hides behind the net's first tower pass.  The overlap happens (net CTAs start 49..178 us into
+// the tick instead of ~105), but a net CTA can only move onto an SM once most of that SM's games are done, the games still
+// running next to it slow down 1.8x (last finish 173 us instead of 97), and the SMs hosting them start their two CTAs last
+// -- with three 170-us unit passes per CTA nothing can be rebalanced at that granularity, so the kernel ends when it did.
 int run_ticks(az_pool *pool, FILE *out, bool copy_records, int ticks, int64_t *games)
 {
     int rc = AZ_OK;
@@ -817,6 +824,8 @@ int run_ticks(az_pool *pool, FILE *out, bool copy_records, int ticks, int64_t *g
                 cudaEventElapsedTime(&b, grp.ev[3 * t + 1], grp.ev[3 * t + 2]) != cudaSuccess) continue;
             pool->tree_seconds += a * 1e-3;
             pool->net_seconds += b * 1e-3;
+            pool->tick_seconds += (a + b) * 1e-3;
+            if (&grp == &pool->groups[0]) pool->timed_ticks++;
             if (t > 0 && cudaEventElapsedTime(&c, grp.ev[3 * t - 1], grp.ev[3 * t]) == cudaSuccess) { grp.trace_gap_ms += c; grp.trace_n++; }
         }
     return AZ_OK;

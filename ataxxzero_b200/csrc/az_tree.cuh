@@ -45,7 +45,6 @@ constexpr int kHintShift = 23;
 constexpr uint32_t kChildMask = 0x00ffffffu;     // Entry::child: node index
 constexpr int kMoveIdxShift = 24;
 constexpr int kNoCand = 0xff;
-constexpr uint32_t kFavValid = 0x80000000u;
 constexpr int kRecWordsPerPly = 6 + 2 * 256;    // worst-case record words per ply
 
 enum : uint32_t {
@@ -69,11 +68,8 @@ struct __align__(16) NodeHdr {
     uint8_t turn;            // absolute side to move: 0 = x, 1 = o
     uint8_t flags;
     uint16_t pad0;
-    uint32_t pad[1];
-    uint32_t fav;            // node index of the child the last selection at this node went to | kFavValid ("favourite":
-    uint32_t fav_k;          // fetched before the scores are known) and the number of entries that child had
+    uint32_t pad[3];
 };
-constexpr int kOffFav = 56;
 static_assert(sizeof(NodeHdr) == 64, "node header is 64 bytes");
 
 struct Entry {
@@ -135,8 +131,6 @@ struct PoolDev {
                              // the first `cap` were evaluated) and zeroes its successor's slot, so the host never memsets.
     float *logits;           // [G][833]
     float *values;           // [G]
-    double *exps;            // [G][833] exp((double)logit), written by the tensor-core net kernel together with ...
-    double *totals;          // [G]      ... their sequential sum; nullptr: the tree kernel computes both itself
     uint32_t *records;       // [G][2][rec_cap_words]
     DoneEntry *done;         // [2G]
     int32_t *done_count;     // [1]
@@ -159,7 +153,6 @@ struct PoolDev {
     int32_t spec_k;          // children requested per consumed node
     int32_t req_cap;         // requests the net kernel serves per tick
     uint32_t tick_id;        // increments with every tick
-    int32_t favourite;       // 1: prefetch the favourite child of every node on the way down (AZ_TREE_FAVOURITE=0 switches it off)
     int32_t force_slow;      // test knob (AZ_TREE_FORCE_SLOW=1): resolve every candidate by the full scan
     unsigned long long *prof;   // AZ_POOL_PROFILE=1: [G][8] clock cycles per phase of the last tick (debug aid, normally nullptr)
 };

@@ -412,7 +412,9 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (net), from CUDA events around its launches ----
     pk, pk_kind = peaks()
+    # net_seconds / tree_seconds: CUDA events around every k_tree_tick and k_net_tc launch of the timed region, summed
     net_s = max(d["net_seconds"], 1e-9)
+    timed = max(d.get("timed_ticks", 0), 1)
     achieved = d["evals"] * FLOP_PER_EVAL / net_s / 1e12
     peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)))
     try:
@@ -422,12 +424,12 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "k_net_tc (bf16 tcgen05 tower)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_note": "dram__bytes_read+write per launch from profiles/ (ncu --set full); the weights stream from L2",
-                "flop_per_launch": d["evals"] / max(d["ticks"], 1) * FLOP_PER_EVAL,
+                "flop_per_launch": d["evals"] / timed * FLOP_PER_EVAL,
                 "peak_kind": "%s bf16_tflops_sustained (kernel timed inside a long step)" % pk_kind,
                 "net_share_of_step": d["net_seconds"] / max(d["net_seconds"] + d["tree_seconds"], 1e-9),
-                "tree_ms_per_tick": d["tree_seconds"] / max(d["ticks"], 1) * 1e3,
-                "net_ms_per_tick": d["net_seconds"] / max(d["ticks"], 1) * 1e3,
-                "timing": "CUDA events around EVERY k_tree_tick and k_net_tc launch of the timed region (summed, not sampled)"}
+                "tree_ms_per_tick": d["tree_seconds"] / timed * 1e3, "net_ms_per_tick": d["net_seconds"] / timed * 1e3,
+                "launches_timed": int(2 * timed),
+                "timing": "CUDA events around EVERY k_tree_tick and k_net_tc launch of the timed region (%d ticks, summed, not sampled)" % timed}
     # tree kernel: HBM roofline on SURVEY 8(d)'s algorithmic bytes of the reference algorithm (13 KB per MCTS step: every
     # child's P/W/n at every level of the selection path, the backup, 833 logits, the new node)
     tree_s = max(d["tree_seconds"], 1e-9)
@@ -543,8 +545,8 @@ def run_ours(args):
             cd = {key: c1[key] - c0[key] for key in c1}
             config3 = {"games": 256, "visits": 400, "positions": cd["positions"], "positions_per_s": cd["positions"] / (cms * 1e-3),
                        "leaf_evals_per_s": cd["evals"] / (cms * 1e-3), "ms_per_tick": cms / max(cd["ticks"], 1),
-                       "tree_ms_per_tick": cd["tree_seconds"] / max(cd["ticks"], 1) * 1e3,
-                       "net_ms_per_tick": cd["net_seconds"] / max(cd["ticks"], 1) * 1e3}
+                       "tree_ms_per_tick": cd["tree_seconds"] / max(cd.get("timed_ticks", 0), 1) * 1e3,
+                       "net_ms_per_tick": cd["net_seconds"] / max(cd.get("timed_ticks", 0), 1) * 1e3}
 
     # ---- BASELINE configs[0]: uniformly random play, 2000 games, on the device (records copied back to the host) ----
     start = rules.set_board(rules.OPEN_FEN)

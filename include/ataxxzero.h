@@ -167,9 +167,11 @@ typedef struct {
     uint64_t max_depth;        /* deepest selection path seen                                     */
     uint64_t kernel_launches;  /* kernels launched by the pool                                    */
     uint64_t record_bytes;     /* game-record bytes copied device -> host                         */
-    double   net_seconds;      /* device time in the net kernel (CUDA events around every launch)  */
-    double   tree_seconds;     /* device time in the tree kernel                                  */
-    uint64_t levels;           /* tree levels walked by completed selections (sum of path lengths) */
+    double   net_seconds;      /* device time in the net kernel: CUDA events around EVERY launch of the self-play loop, summed */
+    double   tree_seconds;     /* ... and in the tree kernel                                                                  */
+    uint64_t levels;           /* tree levels walked by completed selections (sum of path lengths)                            */
+    double   tick_seconds;     /* tree + net of every self-play tick                                                          */
+    uint64_t timed_ticks;      /* ticks behind the three sums (az_selfplay_* only; az_pool_run does not time its ticks)       */
 } az_pool_stats;
 
 int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_pool **out);

@@ -17,4 +17,4 @@ dt = time.perf_counter() - t0; s1 = pool.stats()
 d = {k: s1[k] - s0[k] for k in s1}
 print("G=%d V=%d %s: %.3f ms/tick tree %.3f net %.3f  pos/s %.0f evals/tick %.0f evals/s %.0f steps/tick %.0f" % (
     G, V, " ".join("%s=%s" % (k, v) for k, v in sorted(os.environ.items()) if k.startswith("AZ_")),
-    dt / T * 1e3, d["tree_seconds"] / T * 1e3, d["net_seconds"] / T * 1e3, d["positions"] / dt, d["evals"] / T, d["evals"] / dt, d["steps"] / T), flush=True)
+    dt / T * 1e3, d["tree_seconds"] / max(d["timed_ticks"], 1) * 1e3, d["net_seconds"] / max(d["timed_ticks"], 1) * 1e3, d["positions"] / dt, d["evals"] / T, d["evals"] / dt, d["steps"] / T), flush=True)
