@@ -9,6 +9,9 @@ constexpr float AZ_BN_EPS = 1e-3f;
 #ifndef AZ_NET_CLUSTER_DEFAULT
 #define AZ_NET_CLUSTER_DEFAULT 2
 #endif
+#ifndef AZ_NET_PAIR_DEFAULT
+#define AZ_NET_PAIR_DEFAULT 1
+#endif
 #ifndef AZ_NET_TILES_DEFAULT
 #define AZ_NET_TILES_DEFAULT 1
 #endif   // tf.layers.batch_normalization default epsilon
@@ -30,6 +33,9 @@ struct AzNet {
     // bf16 tensor-core mode (az_net_tc.cu): BN scale folded into the weights, UMMA operand layout
     uint8_t *tc_stream = nullptr;      // [input conv | tower | heads] in the order the TMA producer streams them
     uint8_t *tc_stream16 = nullptr;    // the same stream with IEEE-half operands (AZ_NET_F16)
+    uint8_t *pair_stream = nullptr;    // CTA-pair kernel (az_net_pair.cu): every stage split into the two CTAs' output-channel halves
+    uint8_t *pair_stream16 = nullptr;
+    int tc_pair = 0;                   // 1: plain forward passes run on CTA pairs (tcgen05 cta_group::2)
     int tc_tiles = 2;                  // kernel variant: tiles (of 2 boards) per CTA
     int tc_cluster = 1;                // CTAs per cluster sharing one multicast weight stream
     __nv_bfloat16 *tc_w = nullptr;     // [2*blocks][18 chunks][8 kgroups][128 cout][8 cin]
@@ -54,5 +60,12 @@ int az_net_forward_internal(az_context *ctx, const void *d_in, int in_kind, int 
                             double *d_totals = nullptr, const int *d_out_map = nullptr);
 int az_net_tc_boards_per_round(az_context *ctx, int tiles);   // boards one wave of persistent CTAs evaluates
 void az_net_tc_release(AzNet *net);
+
+// az_net_pair.cu
+int az_net_pair_alloc(AzNet *net);
+int az_net_pair_prepare(az_context *ctx, AzNet *net);
+void az_net_pair_release(AzNet *net);
+int az_net_pair_forward(az_context *ctx, AzNet *net, const void *d_in, int in_kind, int n, float *d_logits, float *d_values, const int *d_count,
+                        cudaStream_t stream, int f16);
 
 enum { AZ_IN_F32 = 0, AZ_IN_POS = 1 };

@@ -850,6 +850,10 @@ int az_net_tc_alloc(AzNet *net)
     AZ_TC_ATTR(1, AZ_IN_F32, 2); AZ_TC_ATTR(1, AZ_IN_POS, 2); AZ_TC_ATTR(2, AZ_IN_F32, 2); AZ_TC_ATTR(2, AZ_IN_POS, 2);
     AZ_TC_ATTR(1, AZ_IN_F32, 4); AZ_TC_ATTR(1, AZ_IN_POS, 4); AZ_TC_ATTR(2, AZ_IN_F32, 4); AZ_TC_ATTR(2, AZ_IN_POS, 4);
 #undef AZ_TC_ATTR
+    int rc = az_net_pair_alloc(net);
+    if (rc) return rc;
+    const char *penv = getenv("AZ_NET_PAIR");
+    net->tc_pair = penv ? (atoi(penv) != 0) : AZ_NET_PAIR_DEFAULT;
     const char *cenv = getenv("AZ_NET_CLUSTER");       // CTAs sharing one weight stream by multicast: 1, 2 or 4
     net->tc_cluster = cenv ? (atoi(cenv) == 4 ? 4 : atoi(cenv) == 2 ? 2 : 1) : AZ_NET_CLUSTER_DEFAULT;
     const char *env = getenv("AZ_NET_TILES");          // tuning knob: 1 = two single-tile CTAs per SM, 2 = one two-tile CTA per SM
@@ -872,11 +876,12 @@ int az_net_tc_prepare(az_context *ctx, AzNet *net)
                                                          net->tc_shift, f16);
     }
     AZ_CUDA(cudaGetLastError());
-    return AZ_OK;
+    return az_net_pair_prepare(ctx, net);
 }
 
 void az_net_tc_release(AzNet *net)
 {
+    az_net_pair_release(net);
     if (net->tc_stream) cudaFree(net->tc_stream);
     if (net->tc_stream16) cudaFree(net->tc_stream16);
     net->tc_stream16 = nullptr;
@@ -940,6 +945,9 @@ static int tc_launch(az_context *ctx, AzNet *net, const void *d_in, int in_kind,
 {
     if (!stream) stream = ctx->stream;
     if (tiles == 0) tiles = net->tc_tiles;
+    // plain forward passes can run on CTA pairs (az_net_pair.cu): half the weight ingest per SM for the same arithmetic
+    if (net->tc_pair && debug_layers < 0 && !d_exps && !d_out_map && !sym8)
+        return az_net_pair_forward(ctx, net, d_in, in_kind, n, d_logits, d_values, d_count, stream, f16);
     TcParams P;
     P.input = d_in;
     P.n = n;
