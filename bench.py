@@ -418,10 +418,10 @@ def run_ours(args):
     achieved = d["evals"] * FLOP_PER_EVAL / net_s / 1e12
     peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)))
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_net_tc"]["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_net_pair"]["dram_bytes_per_launch"]
     except Exception:
         traffic = None
-    roofline = {"bound": "tensor", "kernel": "k_net_tc (bf16 tcgen05 tower)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "tensor", "kernel": "k_net_pair (bf16 tcgen05 cta_group::2 tower on CTA pairs)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_note": "dram__bytes_read+write per launch from profiles/ (ncu --set full); the weights stream from L2",
                 "flop_per_launch": d["evals"] / timed * FLOP_PER_EVAL,
