@@ -412,7 +412,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (net), from CUDA events around its launches ----
     pk, pk_kind = peaks()
-    # net_seconds / tree_seconds: CUDA events around every k_tree_tick and k_net_tc launch of the timed region, summed
+    # net_seconds / tree_seconds: CUDA events around every k_tree_tick and k_net_pair launch of the timed region, summed
     net_s = max(d["net_seconds"], 1e-9)
     timed = max(d.get("timed_ticks", 0), 1)
     achieved = d["evals"] * FLOP_PER_EVAL / net_s / 1e12
@@ -429,7 +429,7 @@ def run_ours(args):
                 "net_share_of_step": d["net_seconds"] / max(d["net_seconds"] + d["tree_seconds"], 1e-9),
                 "tree_ms_per_tick": d["tree_seconds"] / timed * 1e3, "net_ms_per_tick": d["net_seconds"] / timed * 1e3,
                 "launches_timed": int(2 * timed),
-                "timing": "CUDA events around EVERY k_tree_tick and k_net_tc launch of the timed region (%d ticks, summed, not sampled)" % timed}
+                "timing": "CUDA events around EVERY k_tree_tick and k_net_pair launch of the timed region (%d ticks, summed, not sampled)" % timed}
     # tree kernel: HBM roofline on SURVEY 8(d)'s algorithmic bytes of the reference algorithm (13 KB per MCTS step: every
     # child's P/W/n at every level of the selection path, the backup, 833 logits, the new node)
     tree_s = max(d["tree_seconds"], 1e-9)
