@@ -29,6 +29,9 @@ def build_parser():
     parser.add_argument("--max-seconds", metavar="S", type=float, default=0.0, help="Stop after S seconds (0 = no limit).")
     parser.add_argument("--fp32", action="store_true", help="Evaluate with the fp32 reference-accurate kernel instead of bf16 tensor cores.")
     parser.add_argument("--seed", metavar="N", type=int, default=None, help="RNG seed (default: from the clock, like the reference).")
+    parser.add_argument("--one-random-move", action="store_true",
+                        help="The reference's compile-time ONE_RANDOM_MOVE variant (self_play_client.cpp:24): one uniformly random ply per "
+                             "game, greedy play after it, records carry \"random_ply\".")
     return parser
 
 
@@ -48,7 +51,7 @@ def main(argv=None):
     with Context(device=args.device, seed=seed) as ctx:
         net.load_weights(ctx, args.network)
         pool = search.Pool(ctx, 2 * args.buffer_size, args.visits, eval_mode=search.EVAL_FP32 if args.fp32 else search.EVAL_BF16,
-                           noise=True, auto_play=True, seed=seed)
+                           noise=True, auto_play=True, seed=seed, one_random_move=args.one_random_move)
         start, games, last = time.time(), 0, None
         while not stop["flag"]:
             # a few seconds per call so that signals are honoured promptly

@@ -153,7 +153,7 @@ void append_double(std::string &out, double v)
     out += s;
 }
 
-std::string record_to_json(const uint32_t *rec, int words, int plies, int result)
+std::string record_to_json(const uint32_t *rec, int words, int plies, int result, int random_ply_plus_1 = 0)
 {
     std::string boards = "[", dists = "[", moves = "[";
     int w = 0;
@@ -192,7 +192,8 @@ std::string record_to_json(const uint32_t *rec, int words, int plies, int result
         dists += "}";
         w += 6 + 2 * entries;
     }
-    return "{\"boards\":" + boards + "],\"dists\":" + dists + "],\"moves\":" + moves + "],\"result\":" + std::to_string(result) + "}";
+    const std::string random_ply = random_ply_plus_1 > 0 ? ",\"random_ply\":" + std::to_string(random_ply_plus_1 - 1) : "";   // sorted keys
+    return "{\"boards\":" + boards + "],\"dists\":" + dists + "],\"moves\":" + moves + "]" + random_ply + ",\"result\":" + std::to_string(result) + "}";
 }
 
 // Copy out a group's finished games, append them to `out` (may be null: records are dropped), release the buffers.
@@ -227,7 +228,7 @@ int drain_finished(az_pool *pool, Group &grp, FILE *out, int64_t *games_written,
             pool->d2h_bytes += sizeof(uint32_t) * (uint64_t)words;
             for (int i = first; i < last && out; ++i) {
                 const DoneEntry &d = grp.h_done[i];
-                const std::string line = record_to_json(grp.h_stage + grp.h_offsets[i], d.words, d.plies, d.result);
+                const std::string line = record_to_json(grp.h_stage + grp.h_offsets[i], d.words, d.plies, d.result, d.random_ply);
                 if (fwrite(line.data(), 1, line.size(), out) != line.size() || fputc('\n', out) == EOF)
                     return az_fail(AZ_ERR_IO, "short write to the game file");
             }
@@ -380,6 +381,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         D.seed = cfg->seed;
         D.tick_cycles = getenv("AZ_TICK_CYCLES") ? atoi(getenv("AZ_TICK_CYCLES")) : 0;
         D.force_slow = getenv("AZ_TREE_FORCE_SLOW") ? atoi(getenv("AZ_TREE_FORCE_SLOW")) : 0;
+        D.one_random_move = (cfg->auto_play && cfg->one_random_move) ? 1 : 0;
         D.rec_cap_words = rec_cap_words;
         const size_t G = (size_t)D.G;
         rc |= dev_alloc(&D.nodes, G * D.C * kNodeStride, false);

@@ -99,7 +99,10 @@ struct __align__(16) Game {
     // statistics (summed by the host on demand)
     unsigned long long steps, evals, terminal_steps, positions, finished, skipped, max_depth;
     unsigned long long levels;        // tree levels walked by completed selections (sum of path lengths)
+    int32_t random_ply;               // ONE_RANDOM_MOVE games (self_play_client.cpp:515-518): the ply that is played uniformly at random
+    int32_t pad3;
 };
+static_assert(sizeof(Game) == 160, "Game records are 160 bytes");
 
 // Search pools on the tensor-core net may evaluate SPECULATIVELY (az_pool_config::speculate, engine.py:387-392 queues the
 // likely children of a new node the same way): every game owns a small set-associative cache of evaluations keyed by the
@@ -116,7 +119,9 @@ struct __align__(16) CacheTag {
 constexpr int kCacheWays = 4;   // tags of one set share a 128-byte line
 
 struct DoneEntry {
-    int32_t game, buf, words, plies, result, pad[3];
+    int32_t game, buf, words, plies, result;
+    int32_t random_ply;               // + 1; 0: the record has no "random_ply" key
+    int32_t pad[2];
 };
 
 struct PoolDev {
@@ -153,6 +158,7 @@ struct PoolDev {
     int32_t spec_k;          // children requested per consumed node
     int32_t req_cap;         // requests the net kernel serves per tick
     uint32_t tick_id;        // increments with every tick
+    int32_t one_random_move; // the reference's compile-time ONE_RANDOM_MOVE variant of generate_game (self_play_client.cpp:24,515-552)
     int32_t force_slow;      // test knob (AZ_TREE_FORCE_SLOW=1): resolve every candidate by the full scan
     unsigned long long *prof;   // AZ_POOL_PROFILE=1: [G][8] clock cycles per phase of the last tick (debug aid, normally nullptr)
 };

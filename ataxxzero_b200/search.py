@@ -21,7 +21,7 @@ class PoolConfig(C.Structure):
     _fields_ = [("games", C.c_int32), ("visits", C.c_int32), ("max_plies", C.c_int32), ("noise", C.c_int32),
                 ("auto_play", C.c_int32), ("eval_mode", C.c_int32), ("node_capacity", C.c_int32),
                 ("steps_per_tick", C.c_int32), ("seed", C.c_uint64), ("start_fen", C.c_char * 64),
-                ("speculate", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("speculate", C.c_int32), ("one_random_move", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class PoolStats(C.Structure):
@@ -60,7 +60,7 @@ class Pool:
     ``auto_play=True``: self-play generation (sample ~ visits, record, re-root, restart)."""
 
     def __init__(self, ctx, games, visits, eval_mode=EVAL_BF16, noise=False, auto_play=False, max_plies=400, seed=0,
-                 start_fen="", node_capacity=0, steps_per_tick=0, speculate=0):
+                 start_fen="", node_capacity=0, steps_per_tick=0, speculate=0, one_random_move=False):
         self.ctx = ctx
         cfg = PoolConfig()
         cfg.games, cfg.visits, cfg.max_plies = int(games), int(visits), int(max_plies)
@@ -68,6 +68,7 @@ class Pool:
         cfg.node_capacity, cfg.steps_per_tick, cfg.seed = int(node_capacity), int(steps_per_tick), int(seed) & (2**64 - 1)
         cfg.start_fen = start_fen.encode()
         cfg.speculate = int(speculate)
+        cfg.one_random_move = int(bool(one_random_move))
         self.cfg = cfg
         self.games = int(games)
         self._h = _vp()

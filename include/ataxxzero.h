@@ -153,7 +153,11 @@ typedef struct {
                                the evaluations of its `speculate` highest-prior children are requested in the same batch and
                                kept in a per-game cache (engine.py:387-392 queues likely children the same way); a leaf whose
                                position is cached links without waiting for the net.  Visit counts are unchanged.  0 = off */
-    int32_t reserved[3];
+    int32_t one_random_move;/* self-play: the reference's compile-time ONE_RANDOM_MOVE variant of generate_game
+                               (self_play_client.cpp:24,515-552): ply random_ply ~ U{0..119} is played uniformly at random, the plies
+                               before it are sampled ~ visits, the plies after it take the most visited move; records carry
+                               "random_ply" and games that end at or before that ply are skipped (:632-637).  0 = off (as shipped) */
+    int32_t reserved[2];
 } az_pool_config;
 
 typedef struct {

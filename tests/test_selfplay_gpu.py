@@ -78,6 +78,43 @@ def test_visit_targets_respected(tmp_path, ctx, oracle):
             assert any(all(abs(w * N - round(w * N)) < 1e-6 for w in dist.values()) for N in range(64, 64 + 400))
 
 
+def test_one_random_move_variant(tmp_path, ctx, oracle):
+    """ONE_RANDOM_MOVE (self_play_client.cpp:24,515-552, compile-time off in the shipped build): records carry "random_ply"
+    (keys stay sorted), the plies before it are sampled from the visit distribution, the ply AT it is any legal move -- also one
+    the search never visited, which rebuilds the tree (MCTS::play miss, :477-483) -- the plies after it take the most visited move,
+    and games that end at or before that ply are skipped (:632-637)."""
+    from oracle.cpu import START_FEN
+    from ataxxzero_b200 import model, net, search
+    net.load_weights(ctx, model.Network.random_init(seed=0))
+    out = str(tmp_path / "orm.json")
+    with search.Pool(ctx, 256, 32, eval_mode=search.EVAL_BF16, noise=True, auto_play=True, seed=11, one_random_move=True) as pool:
+        stats = pool.selfplay(out, target_games=120, max_seconds=120)
+    assert stats["games_finished"] >= 120 and stats["games_skipped"] > 0          # random_ply ~ U{0..119}: many games end before it
+    lines = open(out).read().splitlines()
+    off_dist = after = 0
+    for ln in lines:
+        game = json.loads(ln)
+        assert list(game.keys()) == ["boards", "dists", "moves", "random_ply", "result"]
+        rp = game["random_ply"]
+        assert 0 <= rp < 120 and rp + 1 < len(game["moves"])
+        p = oracle.set_board(START_FEN)
+        for ply, (board, move, dist) in enumerate(zip(game["boards"], game["moves"], game["dists"])):
+            assert board == oracle.board_json(p) and oracle.result(p) == 0
+            legal = {oracle.move_string(m): m for m in oracle.movegen(p)}
+            assert move in legal and set(dist) <= set(legal)
+            assert abs(sum(dist.values()) - 1.0) < 1e-9
+            if ply == rp:
+                off_dist += move not in dist
+            else:
+                assert move in dist
+                if ply > rp:
+                    assert dist[move] == max(dist.values())
+                    after += 1
+            p = oracle.makemove(p, legal[move])
+        assert oracle.result(p) == game["result"]
+    assert after > 0 and off_dist > 0          # with ~16..60 legal moves and 32 visits most random moves have no edge
+
+
 def test_legacy_link_contract(tmp_path, ctx, oracle):
     """accelerated_generate_games.py's loop, verbatim, on top of ataxxzero_b200.link."""
     import ctypes
