@@ -232,6 +232,34 @@ int az_samples_extract(az_context *ctx, const uint32_t *plies, size_t ply_words,
 int az_samples_extract_dev(az_context *ctx, const void *d_plies, const void *d_offsets, const void *d_meta, int n, void *d_features,
                            void *d_policy, void *d_value);
 
+/* ---------------- training step (model.py:81-101 build_training, model.py:116-142 train / run_on_samples) ---------------- */
+/* One optimisation step of the reference's network on the GPU: conv tower with batch-norm in TRAINING mode (batch
+ * statistics, moving averages updated with decay 0.99), softmax cross-entropy on the 833 policy logits (mean over the
+ * batch) + mean squared value error + 1e-4 * l2_loss of every trainable variable, MomentumOptimizer(lr, 0.9).
+ * bf16 tensor-core operands, fp32 accumulation / master weights / momentum.  128 filters; any block count. */
+typedef struct az_trainer az_trainer;
+int az_trainer_create(az_context *ctx, int max_batch, int blocks, az_trainer **out);
+void az_trainer_destroy(az_trainer *trainer);
+/* `packed`: the vector az_net_load takes.  Like a fresh train.py process (train.py:112-120) the batch-norm gamma / beta
+ * start at 1 / 0 and the momentum accumulators at 0. */
+int az_trainer_load(az_trainer *trainer, const float *packed, size_t count);
+/* network.train(minibatch, learning_rate) (train.py:154-155).  features int8 [n][7][7][4], policies float [n][7][7][17],
+ * values float [n] -- az_samples_extract's outputs; 2 <= n <= max_batch.  losses (optional) = {policy, value,
+ * regularisation} of this minibatch before the update. */
+int az_trainer_step(az_trainer *trainer, const int8_t *features, const float *policies, const float *values, int n, float learning_rate,
+                    float *losses);
+/* run_on_samples(policy_loss.eval / value_loss.eval) (train.py:141-142): is_training = False (moving statistics), any n.
+ * losses = {policy, value}; logits [n][833] and values_out [n] are optional (NULL to skip). */
+int az_trainer_eval(az_trainer *trainer, const int8_t *features, const float *policies, const float *values, int n, float *losses, float *logits,
+                    float *values_out);
+/* model.save_model (model.py:173-183): weights + moving statistics back in az_net_load's order (gamma / beta are not part
+ * of the file format) */
+int az_trainer_export(az_trainer *trainer, float *packed, size_t count);
+unsigned long long az_trainer_launches(const az_trainer *trainer);
+/* test hook: an internal tensor of the last step ("z", "act", "d_h", "grad_conv", "grad_gamma", "grad_beta", "gamma", "beta",
+ * "conv", "moving", "grad_heads"), see az_train.cu */
+int az_trainer_debug_read(az_trainer *trainer, const char *what, int layer, int n, float *out, size_t count);
+
 /* ---------------- legacy 4-function ABI (link.py:8-32; self_play_client.cpp:683,708,723,740) -------- */
 /* Same names, arguments and blocking behaviour.  The trees live on GPU 0 (or $AZ_DEVICE); the caller is
  * the evaluator: get_workload() fills fill_buffer{1,2} with `buffer_entries` feature planes and returns the

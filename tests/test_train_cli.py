@@ -1,7 +1,11 @@
-"""cli/train.py (last row): the torch restatement of model.py's network equals the NumPy oracle in inference
-form, the loss follows model.py:81-96, a short run lowers it, and the written .npy has the reference layout."""
+"""Training side (last row).  CPU part: the checker itself is pinned -- the fp32 PyTorch restatement of model.py's
+network (tests/torch_train_reference.py) equals the NumPy oracle in inference form and its loss follows model.py:81-96; the
+sampling / encoding rules of train.py:43-77 reproduce the reference goldens; cli/train.py refuses to run without the GPU
+library.  The hand-written training step itself is checked on the GPU (tests/test_train_gpu.py)."""
 import json
 import random
+
+import pytest
 
 import numpy as np
 
@@ -11,7 +15,7 @@ from conftest import load_golden
 def test_torch_network_matches_numpy_restatement():
     import torch
     from ataxxzero_b200 import model
-    from ataxxzero_b200.cli import train
+    import torch_train_reference as train
     from oracle import net_numpy
     network = model.Network.random_init(seed=3, filters=16, blocks=2)
     network.bn = net_numpy.randomize_bn(network.bn, seed=4)
@@ -29,15 +33,15 @@ def test_torch_network_matches_numpy_restatement():
     assert all(np.allclose(a, b) for a, b in zip(back.bn, network.bn))
 
 
-def test_loss_definition_and_short_training_run(tmp_path):
+def test_loss_definition_and_sampling_goldens(tmp_path):
     import torch
     from ataxxzero_b200 import model
-    from ataxxzero_b200.cli import train
+    import torch_train_reference as train
     g = load_golden("train_samples_golden.json")
     games = tmp_path / "games.json"
     games.write_text("\n".join(json.dumps(e) for e in g["entries"] * 4) + "\n")
     # host minibatches (no GPU here) agree with the reference goldens: same picks -> same tensors
-    fn = train.make_minibatch_fn(g["entries"], None)
+    fn = train.host_minibatch_fn(g["entries"])
     class Scripted(random.Random):
         pass
     for s in g["samples"][:20]:
@@ -63,19 +67,23 @@ def test_loss_definition_and_short_training_run(tmp_path):
     want_vl = float(np.mean((batch[2].numpy() - out.numpy()) ** 2))
     want_reg = 0.0001 * sum(0.5 * float((p.detach().numpy().astype(np.float64) ** 2).sum()) for p in net.parameters())
     assert abs(float(pl) - want_pl) < 1e-5 and abs(float(vl) - want_vl) < 1e-6 and abs(float(reg) - want_reg) < 1e-7
-    # a short run: the value loss on the held-in set goes down, and the output file has the reference layout
+
+
+def test_train_cli_needs_the_gpu_library(tmp_path):
+    """No CPU training path: without a visible B200 the CLI stops at az_create instead of falling back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from ataxxzero_b200 import AzError, model
+    from ataxxzero_b200.cli import train
+    g = load_golden("train_samples_golden.json")
+    games = tmp_path / "games.json"
+    games.write_text("\n".join(json.dumps(e) for e in g["entries"] * 2) + "\n")
     old = tmp_path / "model-001.npy"
-    new = tmp_path / "model-002.npy"
-    model.Network.random_init(seed=5, filters=8, blocks=1).save(str(old))
-    hist = train.main(["--games", str(games), "--old-path", str(old), "--new-path", str(new), "--steps", "60",
-                       "--minibatch-size", "64", "--learning-rate", "0.01"])
-    assert hist[-1][0] + hist[-1][1] < hist[0][0] + hist[0][1]
-    trained = model.Network.load(str(new))
-    assert trained.filters == 8 and trained.blocks == 1 and len(trained.bn) == 6
-    assert not np.array_equal(trained.conv[0], model.Network.load(str(old)).conv[0])
-
-
-import pytest
+    model.Network.random_init(seed=5, blocks=1).save(str(old))
+    with pytest.raises((AzError, ImportError)):
+        train.main(["--games", str(games), "--old-path", str(old), "--new-path", str(tmp_path / "model-002.npy"), "--steps", "2"])
+    assert not (tmp_path / "model-002.npy").exists()
 
 
 @pytest.mark.gpu

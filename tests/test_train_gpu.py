@@ -1,0 +1,181 @@
+"""The hand-written training step (csrc/az_train.cu behind ataxxzero_b200/trainer.py) against the fp32 PyTorch restatement of
+the reference's training graph (tests/torch_train_reference.py; model.py:35-101).
+
+Operands are bf16 (8 mantissa bits) with fp32 accumulation, so the comparison is by tolerance, stated per quantity:
+  * forward conv outputs / activations: relative L2 error <= 2e-2 per layer (measured 2e-3 .. 6e-3 over 5 layers);
+  * losses of the step: |policy| <= 2e-3, |value| <= 5e-3, regularisation relative 1e-5 (fp32 either side);
+  * gradients: cosine similarity >= 0.98 and norm ratio within 3 % per tensor.  At random init with random targets a weight
+    gradient is a sum of ~n*49 terms of mixed sign that cancels to ~1/50 of its terms' size, which amplifies the operands'
+    0.4 % rounding to a few percent of the (small) sum: measured 5..9 % relative L2 error = cosine 0.996;
+  * 30 optimiser steps on a fixed batch: the loss trajectory follows PyTorch's within 2e-3 at every step.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def synthetic_batch(n, seed):
+    rng = np.random.default_rng(seed)
+    feats = np.zeros((n, 7, 7, 4), np.int8)
+    feats[..., 0] = 1
+    who = rng.integers(0, 3, size=(n, 7, 7))
+    feats[..., 1] = who == 1
+    feats[..., 2] = who == 2
+    pol = rng.random((n, 7, 7, 17)).astype(np.float32) ** 8
+    pol /= pol.reshape(n, -1).sum(1).reshape(n, 1, 1, 1)
+    val = rng.choice([-1.0, 1.0], size=(n, 1)).astype(np.float32)
+    return feats, pol, val
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def cosine(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-30))
+
+
+def torch_setup(network, blocks, lr):
+    import torch
+    import torch_train_reference as ref
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    net = ref.build_torch_network(128, blocks).to(dev)
+    ref.load_into(net, network)
+    net.train()
+    return ref, net, torch.optim.SGD(net.parameters(), lr=lr, momentum=0.9), dev
+
+
+@pytest.mark.parametrize("blocks,n", [(2, 64), (1, 37)])
+def test_one_step_matches_fp32_restatement(ctx, blocks, n):
+    """Forward tensors, the three loss terms, every gradient tensor and the updated weights of ONE step; n = 37 leaves half a
+    tile empty (odd batch) and several tile ranges of the weight-gradient kernel without work."""
+    import torch
+    import torch.nn.functional as Fn
+    from ataxxzero_b200 import model, trainer
+    lr, lam = 0.01, 1e-4
+    network = model.Network.random_init(seed=5, blocks=blocks)
+    ref, net, opt, dev = torch_setup(network, blocks, lr)
+    tr = trainer.Trainer(ctx, network, max_batch=64)
+    batch = synthetic_batch(n, 1)
+    x, pol, val = ref.to_torch_batch(batch, dev)
+    zs, acts = [], []
+
+    def conv_bn(i, inp):
+        z = net.convs[i](inp)
+        zs.append(z)
+        return net.bns[i](z)
+    h = Fn.relu(conv_bn(0, x))
+    acts.append(h)
+    for b in range(blocks):
+        y = Fn.relu(conv_bn(1 + 2 * b, h))
+        acts.append(y)
+        h = Fn.relu(conv_bn(2 + 2 * b, y) + h)
+        acts.append(h)
+    logits = net.policy(h).permute(0, 2, 3, 1).reshape(n, -1)
+    v = torch.tanh(net.value(h).permute(0, 2, 3, 1).reshape(n, 49) @ net.fc_w + net.fc_b)
+    pl = -(pol.reshape(n, -1) * torch.log_softmax(logits, dim=1)).sum(1).mean()
+    vl = ((val - v) ** 2).mean()
+    reg = lam * sum(0.5 * (p ** 2).sum() for p in net.parameters())
+    opt.zero_grad()
+    (pl + vl + reg).backward()
+
+    ours = tr.train(*batch, learning_rate=lr)
+    assert abs(ours[0] - float(pl)) < 2e-3 and abs(ours[1] - float(vl)) < 5e-3 and abs(ours[2] - float(reg)) < 1e-5 * float(reg) + 1e-7
+    layers = 1 + 2 * blocks
+    for l in range(layers):
+        assert rel(tr.debug_read("z", l, n), zs[l].detach().permute(0, 2, 3, 1).cpu().numpy()) < 2e-2, l
+        assert rel(tr.debug_read("act", l + 1, n), acts[l].detach().permute(0, 2, 3, 1).cpu().numpy()) < 2e-2, l
+    for l in range(layers):
+        w = net.convs[l].weight
+        g_ref = (w.grad - lam * w).detach().permute(2, 3, 1, 0).cpu().numpy()          # TF order [kx][ky][cin][cout], L2 term removed
+        g = tr.debug_read("grad_conv", l)
+        if l == 0:
+            assert not g[:, :, 4:, :].any()                                              # padded input channels stay exactly zero
+            g = g[:, :, :4, :]
+        assert cosine(g, g_ref) > 0.98 and abs(np.linalg.norm(g) / np.linalg.norm(g_ref) - 1) < 0.03, l
+        for name, p in (("grad_gamma", net.bns[l].weight), ("grad_beta", net.bns[l].bias)):
+            assert cosine(tr.debug_read(name, l), (p.grad - lam * p).detach().cpu().numpy()) > 0.98, (name, l)
+    gh = tr.debug_read("grad_heads")
+    assert rel(gh[:128 * 17].reshape(128, 17), (net.policy.weight.grad - lam * net.policy.weight).detach().reshape(17, 128).t().cpu().numpy()) < 2e-2
+    assert rel(gh[128 * 17:128 * 18], (net.value.weight.grad - lam * net.value.weight).detach().reshape(128).cpu().numpy()) < 3e-2
+    assert rel(gh[128 * 18:128 * 18 + 49], (net.fc_w.grad - lam * net.fc_w).detach().reshape(49).cpu().numpy()) < 3e-2
+    assert rel(gh[-1:], (net.fc_b.grad - lam * net.fc_b).detach().cpu().numpy()) < 1e-2
+    opt.step()
+    for l in range(layers):
+        w_ref = net.convs[l].weight.detach().permute(2, 3, 1, 0).cpu().numpy()
+        w = tr.debug_read("conv", l)
+        assert rel(w[:, :, :4, :] if l == 0 else w, w_ref) < 5e-3, l
+    mv = tr.debug_read("moving", 1)                                                     # update ops: decay 0.99, unbiased variance
+    assert rel(mv[0], net.bns[1].running_mean.cpu().numpy()) < 2e-2 and rel(mv[1], net.bns[1].running_var.cpu().numpy()) < 1e-4
+    tr.close()
+
+
+def test_fixed_batch_run_follows_fp32_trajectory_and_export_round_trips(ctx, tmp_path):
+    """30 momentum steps on one batch: the loss curve follows PyTorch's; the exported .npy feeds the inference kernels, whose
+    fp32 forward reproduces the trainer's eval-mode outputs when gamma = 1 / beta = 0 (fresh load, no step taken)."""
+    from ataxxzero_b200 import model, net as aznet, trainer
+    blocks, n, lr = 2, 64, 0.01
+    network = model.Network.random_init(seed=7, blocks=blocks)
+    ref, net, opt, dev = torch_setup(network, blocks, lr)
+    tr = trainer.Trainer(ctx, network, max_batch=n)
+    batch = synthetic_batch(n, 3)
+    # eval mode before any step == the library's own inference on the same weights
+    pe, ve, logits, values = tr.losses(*batch, outputs=True)
+    aznet.load_weights(ctx, network)
+    lg, vv = aznet.forward(ctx, batch[0].astype(np.float32), mode=aznet.FP32)
+    assert np.abs(logits - lg.reshape(logits.shape)).max() < 2e-2 and np.abs(values.reshape(-1) - vv.reshape(-1)).max() < 2e-2
+    xb = ref.to_torch_batch(batch, dev)
+    ours, theirs = [], []
+    for _ in range(30):
+        lo = tr.train(*batch, learning_rate=lr)
+        p2, v2, r2 = ref.loss_terms(net, *xb)
+        opt.zero_grad()
+        (p2 + v2 + r2).backward()
+        opt.step()
+        ours.append(lo[0] + lo[1])
+        theirs.append(float(p2.detach() + v2.detach()))
+    assert np.abs(np.array(ours) - np.array(theirs)).max() < 2e-3, (ours, theirs)
+    assert ours[-1] < ours[0] - 0.5
+    # eval-mode losses use the moving statistics (is_training = False), any batch size, odd sizes and slices included
+    big = synthetic_batch(150, 4)
+    p_all, v_all = tr.losses(*big)
+    parts = [tr.losses(big[0][a:b], big[1][a:b], big[2][a:b]) for a, b in ((0, 64), (64, 128), (128, 150))]
+    want_p = (parts[0][0] * 64 + parts[1][0] * 64 + parts[2][0] * 22) / 150
+    assert abs(p_all - want_p) < 1e-4 and np.isfinite(v_all)
+    out = tr.network()
+    path = tmp_path / "model-002.npy"
+    model.save_model(out, str(path))
+    back = model.Network.load(str(path))
+    assert back.blocks == blocks and all(np.array_equal(a, b) for a, b in zip(back.conv, out.conv))
+    assert not np.array_equal(back.conv[1], network.conv[1]) and not np.array_equal(back.bn[0], network.bn[0])
+    tr.close()
+
+
+def test_full_size_step_and_argument_checks(ctx):
+    """The reference's shape (128 filters x 12 blocks, minibatch 512): finite losses that fall over a few steps; bad calls fail."""
+    from ataxxzero_b200 import AzError, model, trainer
+    network = model.Network.random_init(seed=1)
+    tr = trainer.Trainer(ctx, network, max_batch=512)
+    batch = synthetic_batch(512, 9)
+    first = tr.train(*batch, learning_rate=0.01)
+    for _ in range(10):
+        last = tr.train(*batch, learning_rate=0.01)
+    assert all(np.isfinite(first)) and last[0] + last[1] < first[0] + first[1]
+    assert tr.launches > 0
+    with pytest.raises(AzError):
+        tr.train(batch[0][:1], batch[1][:1], batch[2][:1], learning_rate=0.01)          # a batch-norm batch of one board
+    big = synthetic_batch(514, 2)
+    with pytest.raises(AzError):
+        tr.train(*big, learning_rate=0.01)                                               # beyond max_batch
+    with pytest.raises(AzError):
+        tr.train(*batch, learning_rate=float("nan"))
+    with pytest.raises(ValueError):
+        trainer.Trainer(ctx, model.Network.random_init(seed=1, filters=64, blocks=1))
+    tr.close()

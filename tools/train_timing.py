@@ -1,0 +1,20 @@
+"""Steady-state timing of the hand-written training step (reference shape: 128 filters x 12 blocks, minibatch 512)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import ataxxzero_b200 as az
+from ataxxzero_b200 import model, trainer
+from test_train_gpu import synthetic_batch
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+ctx = az.Context(0)
+tr = trainer.Trainer(ctx, model.Network.random_init(seed=1), max_batch=N)
+batch = synthetic_batch(N, 2)
+for _ in range(3):
+    tr.train(*batch, learning_rate=1e-3)
+t0 = time.perf_counter(); l0 = tr.launches
+for _ in range(STEPS):
+    tr.train(*batch, learning_rate=1e-3)
+dt = (time.perf_counter() - t0) / STEPS
+print("native step %d boards x 12 blocks: %.3f ms/step, %.0f samples/s, %d launches/step" % (N, dt * 1e3, N / dt, (tr.launches - l0) // STEPS))
