@@ -21,8 +21,8 @@
 //               and input / output channels swapped.
 //   k_wgrad     weight gradient dW[tap][ci][co] = sum_r in[r + shift(tap)][ci] * dz[r][co]: the contraction runs over ROWS,
 //               so both operands are read MN-major straight from the same tile-blocked images (no transposes anywhere);
-//               a CTA owns three taps (three 128-column accumulators) and a range of tiles, and adds its partial sums
-//               to the gradient with fp32 reductions.
+//               a CTA owns three taps (three 128-column accumulators) and a range of tiles and writes its partial sums;
+//               k_wgrad_reduce adds the ranges up in a fixed order.
 //   k_bn_*      batch statistics (fp64 sums), normalise + residual + ReLU, and the two passes of the batch-norm backward.
 //   k_heads     per board: policy / value heads, losses, their gradients, the gradient flowing into the tower.
 //   k_sgd       L2 term + momentum update, then k_images re-tiles the new weights into the two bf16 operand images.
@@ -73,6 +73,10 @@ __device__ __forceinline__ bool row_is_real(int r, int &board_in_tile, int &cell
     return w >= 8 && y != 7;
 }
 __host__ __device__ __forceinline__ int tap_shift(int tap) { return (tap / 3 - 1) * 8 + (tap % 3 - 1); }
+__device__ __forceinline__ uint4 load_bf8(const uint8_t *tb16, int tile, int kg, int row)
+{
+    return *reinterpret_cast<const uint4 *>(tb16 + (size_t)tile * TB16_TILE + kg * SLICE_BYTES + row * ROW_BYTES);
+}
 
 // ------------------------------------------------------------------------------------------
 // k_conv: forward convolution / data gradient of one layer, one CTA per tile
@@ -91,7 +95,29 @@ struct ConvParams {
     const uint8_t *w;        // weight image of the layer
     float *out;              // TB32
     int accumulate;          // 1: out += result (the skip connection's gradient is already there)
+    double *stats;           // optional [2][F]: per-channel sum / sum of squares of the result are added (batch-norm statistics)
+    // data-gradient launches: the result is the gradient w.r.t. the OUTPUT of the layer below; the first pass of that
+    // layer's batch-norm backward (sum g, sum g * xhat with g = result masked by the ReLU) is taken here, in registers
+    const uint8_t *below_act;      // TB16 output activation of the layer below (ReLU mask); nullptr: no fused statistics
+    const float *below_z;          // TB32 its conv output
+    const float *below_mean_rstd;  // [2][F]
+    double *below_sums;            // [2][F]
 };
+
+// column sums of a 32 x 32 block held one row per lane: after five exchange-and-add steps lane c holds the sum of column c
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane)
+{
+#pragma unroll
+    for (int half = 16; half; half >>= 1) {
+        const bool upper = lane & half;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = upper ? v[i + half] : v[i], send = upper ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
 
 __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv(const ConvParams P)
 {
@@ -157,19 +183,63 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv(const ConvParams P)
         mbar_wait(bar(B_ACC), 0);
         tc_fence_after();
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        float *part = reinterpret_cast<float *>(smem);  // [4 warps][2][F] column sums; the staged input is dead by now
+        const bool sums = P.stats || P.below_act;
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
             uint32_t a[32];
             tmem_ld32(lane_addr + q * 32, a);
             tmem_wait_ld();
+            float v[32];
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                float4 v = real ? make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]))
+                float4 o = real ? make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]))
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 *p = reinterpret_cast<float4 *>(dst + (q * 8 + g) * TILE_M * 4);
-                if (P.accumulate) { const float4 o = *p; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                *p = v;
+                if (P.accumulate) { const float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                *p = o;
+                v[4 * g] = o.x; v[4 * g + 1] = o.y; v[4 * g + 2] = o.z; v[4 * g + 3] = o.w;
             }
+            if (sums) {
+                float w[32];
+                if (P.stats) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
+                } else {
+                    // g = gradient where the layer below was active; w = g * xhat of the layer below
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint4 m = load_bf8(P.below_act, tile, q * 4 + g, r);
+                        const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (!(bf16_lo(mw[i]) > 0.f)) v[8 * g + 2 * i] = 0.f;
+                            if (!(bf16_hi(mw[i]) > 0.f)) v[8 * g + 2 * i + 1] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 z = *reinterpret_cast<const float4 *>(P.below_z + (size_t)tile * TB32_TILE_F + ((q * 8 + g) * TILE_M + r) * 4);
+                        const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int c = q * 32 + 4 * g + i;
+                            w[4 * g + i] = v[4 * g + i] * ((zz[i] - __ldg(P.below_mean_rstd + c)) * __ldg(P.below_mean_rstd + F + c));
+                        }
+                    }
+                }
+                part[(quad * 2 + 0) * F + q * 32 + lane] = warp_column_sums(v, lane);
+                part[(quad * 2 + 1) * F + q * 32 + lane] = warp_column_sums(w, lane);
+            }
+        }
+        if (sums) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            double *dst_sums = P.stats ? P.stats : P.below_sums;
+            const int c = (warp - 2) * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                atomicAdd(dst_sums + k * F + c, (double)part[(0 * 2 + k) * F + c] + (double)part[(1 * 2 + k) * F + c] + (double)part[(2 * 2 + k) * F + c] +
+                                                    (double)part[(3 * 2 + k) * F + c]);
         }
     }
     tc_fence_before();
@@ -193,7 +263,7 @@ constexpr int WG_RANGES = 48;                                        // 48 x 3 =
 struct WgradParams {
     const uint8_t *in;       // TB16: the layer's input activations
     const uint8_t *dz;       // TB16: gradient w.r.t. the layer's conv output
-    float *dw;               // [9][F][F] fp32, added to
+    float *partial;          // [ranges][9][F][F] fp32: every CTA writes the sums over its own tiles (k_wgrad_reduce adds them up)
     int tiles;
 };
 
@@ -203,7 +273,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const WgradParams P)
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = (int)((long long)P.tiles * blockIdx.x / gridDim.x), t1 = (int)((long long)P.tiles * (blockIdx.x + 1) / gridDim.x);
-    if (t0 >= t1) return;                               // more ranges than tiles: nothing to add
+    if (t0 >= t1) return;                               // (the host launches at most one range per tile)
     const int tap0 = blockIdx.y * WG_TAPS;
     auto bar = [&](int i) { return sbase + WG_OFF_BAR + 8 * i; };
     constexpr int B_FULL = 0, B_EMPTY = WG_STAGES, B_ACC = 2 * WG_STAGES;
@@ -267,20 +337,36 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const WgradParams P)
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
         for (int j = 0; j < WG_TAPS; ++j) {
-            float *dst = P.dw + ((size_t)(tap0 + j) * F + ci) * F;
+            float *dst = P.partial + (size_t)blockIdx.x * LAYER_W + ((size_t)(tap0 + j) * F + ci) * F;
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {
                 uint32_t a[32];
                 tmem_ld32(lane_addr + j * 128 + q * 32, a);
                 tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(dst + q * 32 + i, __uint_as_float(a[i]));
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4 *>(dst + q * 32 + 4 * i) =
+                        make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]), __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// dw[i] = sum over the row ranges of partial[range][i], in range order (deterministic)
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float *__restrict__ partial, float *__restrict__ dw, int ranges)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // float4 index
+    if (i >= LAYER_W / 4) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int r = 0; r < ranges; ++r) {
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(partial + (size_t)r * LAYER_W) + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4 *>(dw)[i] = acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -296,10 +382,6 @@ __device__ __forceinline__ void store8(float *tb32, int tile, int kg, int row, c
 {
     *reinterpret_cast<float4 *>(tb32 + (size_t)tile * TB32_TILE_F + ((2 * kg) * TILE_M + row) * 4) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4 *>(tb32 + (size_t)tile * TB32_TILE_F + ((2 * kg + 1) * TILE_M + row) * 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ uint4 load_bf8(const uint8_t *tb16, int tile, int kg, int row)
-{
-    return *reinterpret_cast<const uint4 *>(tb16 + (size_t)tile * TB16_TILE + kg * SLICE_BYTES + row * ROW_BYTES);
 }
 __device__ __forceinline__ void store_bf8(uint8_t *tb16, int tile, int kg, int row, const float (&v)[8])
 {
@@ -338,22 +420,6 @@ __global__ void __launch_bounds__(128) k_stage_input(const int8_t *__restrict__ 
         v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
     }
     store_bf8(act0, tile, 0, row, v);
-}
-
-// batch statistics of a conv output: sum and sum of squares per channel over the real cells (padding rows hold zeros)
-__global__ void __launch_bounds__(128) k_bn_stats(const float *__restrict__ z, double *__restrict__ sums, int tiles)
-{
-    const int kg = blockIdx.x, row = threadIdx.x;
-    float acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-    for (int tile = blockIdx.y; tile < tiles; tile += gridDim.y) {
-        float v[8];
-        load8(z, tile, kg, row, v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[i] += v[i]; acc[8 + i] += v[i] * v[i]; }
-    }
-    block_sum16_to_global(acc, sums, sums + F, kg);
 }
 
 struct BnApplyParams {
@@ -690,7 +756,7 @@ struct az_trainer {
     size_t off_gamma = 0, off_beta = 0, off_policy = 0, off_value = 0, off_fcw = 0, off_fcb = 0;
     float *theta = nullptr, *mom = nullptr, *grad = nullptr, *moving = nullptr, *mean_rstd = nullptr;
     uint8_t *img_f = nullptr, *img_b = nullptr, *act = nullptr, *dz = nullptr;
-    float *z = nullptr, *h32 = nullptr, *d_h = nullptr, *d_y = nullptr;
+    float *z = nullptr, *h32 = nullptr, *d_h = nullptr, *d_y = nullptr, *wg_partial = nullptr;
     double *fsum = nullptr, *bsum = nullptr, *loss = nullptr;
     int8_t *d_feats = nullptr;
     float *d_pol = nullptr, *d_val = nullptr, *d_logits = nullptr, *d_values_out = nullptr;
@@ -731,9 +797,9 @@ int forward(az_trainer *t, int n, bool train, bool want_outputs)
     k_stage_input<<<tiles, 128, 0, s>>>(t->d_feats, t->act_at(0), n);
     t->launches++;
     for (int l = 0; l < t->layers; ++l) {
-        ConvParams C{t->act_at(l), t->img_f + (size_t)l * LAYER_IMG_BYTES, t->z_at(l), 0};
+        // training: the conv epilogue also adds up the batch statistics of its output
+        ConvParams C{t->act_at(l), t->img_f + (size_t)l * LAYER_IMG_BYTES, t->z_at(l), 0, train ? t->fsum + (size_t)l * 2 * F : nullptr, nullptr, nullptr, nullptr, nullptr};
         k_conv<<<tiles, CONV_THREADS, CONV_SMEM, s>>>(C);
-        if (train) k_bn_stats<<<ew, 128, 0, s>>>(t->z_at(l), t->fsum + (size_t)l * 2 * F, tiles);
         BnApplyParams B{};
         B.z = t->z_at(l);
         B.sums = t->fsum + (size_t)l * 2 * F;
@@ -748,7 +814,7 @@ int forward(az_trainer *t, int n, bool train, bool want_outputs)
         B.n = n;
         B.use_moving = train ? 0 : 1;
         k_bn_apply<<<ew, 128, 0, s>>>(B);
-        t->launches += train ? 3 : 2;
+        t->launches += 2;
     }
     HeadsParams H{};
     H.h32 = t->h32;
@@ -795,14 +861,20 @@ int backward(az_trainer *t, int n)
         B.write_g = second ? 1 : 0;                     // the masked gradient also flows down the skip connection
         B.tiles = tiles;
         B.n = n;
-        k_bn_bwd_stats<<<ew, 128, 0, s>>>(B);
+        if (l == t->layers - 1) {                       // every other layer's sums come out of the data-gradient epilogue above it
+            k_bn_bwd_stats<<<ew, 128, 0, s>>>(B);
+            t->launches++;
+        }
         k_bn_bwd_apply<<<ew, 128, 0, s>>>(B);
-        WgradParams W{t->act_at(l), t->dz, t->grad + (size_t)l * LAYER_W, tiles};
-        k_wgrad<<<dim3(WG_RANGES, 9 / WG_TAPS), WG_THREADS, WG_SMEM, s>>>(W);
+        const int ranges = std::min(WG_RANGES, tiles);       // every range owns at least one tile
+        WgradParams W{t->act_at(l), t->dz, t->wg_partial, tiles};
+        k_wgrad<<<dim3(ranges, 9 / WG_TAPS), WG_THREADS, WG_SMEM, s>>>(W);
+        k_wgrad_reduce<<<LAYER_W / 4 / 256, 256, 0, s>>>(t->wg_partial, t->grad + (size_t)l * LAYER_W, ranges);
         t->launches += 3;
         if (l > 0) {
             // data gradient: into d_y for the second conv of a block, ON TOP of the skip gradient in d_h for the first
-            ConvParams C{t->dz, t->img_b + (size_t)l * LAYER_IMG_BYTES, first ? t->d_h : t->d_y, first ? 1 : 0};
+            ConvParams C{t->dz, t->img_b + (size_t)l * LAYER_IMG_BYTES, first ? t->d_h : t->d_y, first ? 1 : 0, nullptr,
+                         t->act_at(l), t->z_at(l - 1), t->mean_rstd + (size_t)(l - 1) * 2 * F, t->bsum + (size_t)(l - 1) * 2 * F};
             k_conv<<<tiles, CONV_THREADS, CONV_SMEM, s>>>(C);
             t->launches++;
         }
@@ -855,6 +927,7 @@ extern "C" int az_trainer_create(az_context *ctx, int max_batch, int blocks, az_
     rc |= dev_alloc(&t->h32, T * TB32_TILE_F);
     rc |= dev_alloc(&t->d_h, T * TB32_TILE_F);
     rc |= dev_alloc(&t->d_y, T * TB32_TILE_F);
+    rc |= dev_alloc(&t->wg_partial, (size_t)WG_RANGES * LAYER_W);
     rc |= dev_alloc(&t->fsum, L * 2 * F);
     rc |= dev_alloc(&t->bsum, L * 2 * F);
     rc |= dev_alloc(&t->loss, 4);
@@ -877,7 +950,7 @@ extern "C" void az_trainer_destroy(az_trainer *t)
     if (!t) return;
     cudaStreamSynchronize(t->ctx->stream);
     void *bufs[] = {t->theta, t->mom, t->grad, t->moving, t->mean_rstd, t->img_f, t->img_b, t->act, t->dz, t->z, t->h32, t->d_h, t->d_y,
-                    t->fsum, t->bsum, t->loss, t->d_feats, t->d_pol, t->d_val, t->d_logits, t->d_values_out};
+                    t->fsum, t->bsum, t->loss, t->wg_partial, t->d_feats, t->d_pol, t->d_val, t->d_logits, t->d_values_out};
     for (void *p : bufs) cudaFree(p);
     if (t->h_loss) cudaFreeHost(t->h_loss);
     delete t;
