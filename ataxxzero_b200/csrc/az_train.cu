@@ -335,9 +335,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const WgradParams P)
         mbar_wait(bar(B_ACC), 0);
         tc_fence_after();
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        // partial sums are stored [tap][group of 4 output channels][input channel][4]: the 32 lanes of a warp (consecutive
+        // input channels) write 512 contiguous bytes per store
 #pragma unroll 1
         for (int j = 0; j < WG_TAPS; ++j) {
-            float *dst = P.partial + (size_t)blockIdx.x * LAYER_W + ((size_t)(tap0 + j) * F + ci) * F;
+            float *dst = P.partial + (size_t)blockIdx.x * LAYER_W + (size_t)(tap0 + j) * F * F + ci * 4;
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {
                 uint32_t a[32];
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const WgradParams P)
                 tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    *reinterpret_cast<float4 *>(dst + q * 32 + 4 * i) =
+                    *reinterpret_cast<float4 *>(dst + (q * 8 + i) * F * 4) =
                         make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]), __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
             }
         }
@@ -355,18 +357,33 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const WgradParams P)
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// dw[i] = sum over the row ranges of partial[range][i], in range order (deterministic)
-__global__ void __launch_bounds__(256) k_wgrad_reduce(const float *__restrict__ partial, float *__restrict__ dw, int ranges)
+// dw[i] = sum over the row ranges of partial[range][i], always in the same order (deterministic).  A block covers 64 float4
+// columns; its four thread rows each add a quarter of the ranges, all loads of a quarter in flight together.
+constexpr int WGR_COLS = 64, WGR_SPLIT = 4, WGR_PER = WG_RANGES / WGR_SPLIT;
+static_assert(WG_RANGES % WGR_SPLIT == 0, "ranges split evenly");
+__global__ void __launch_bounds__(WGR_COLS * WGR_SPLIT) k_wgrad_reduce(const float *__restrict__ partial, float *__restrict__ dw, int ranges)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // float4 index
-    if (i >= LAYER_W / 4) return;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-    for (int r = 0; r < ranges; ++r) {
-        const float4 v = __ldcg(reinterpret_cast<const float4 *>(partial + (size_t)r * LAYER_W) + i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    __shared__ float4 part[WGR_SPLIT][WGR_COLS];
+    const int col = threadIdx.x % WGR_COLS, quarter = threadIdx.x / WGR_COLS;
+    const int i = blockIdx.x * WGR_COLS + col;                    // float4 index
+    float4 v[WGR_PER];
+#pragma unroll
+    for (int k = 0; k < WGR_PER; ++k) {
+        const int r = quarter * WGR_PER + k;
+        v[k] = r < ranges ? __ldcg(reinterpret_cast<const float4 *>(partial + (size_t)r * LAYER_W) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    reinterpret_cast<float4 *>(dw)[i] = acc;
+    float4 acc = v[0];
+#pragma unroll
+    for (int k = 1; k < WGR_PER; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    part[quarter][col] = acc;
+    __syncthreads();
+    if (quarter == 0) {
+#pragma unroll
+        for (int k = 1; k < WGR_SPLIT; ++k) { acc.x += part[k][col].x; acc.y += part[k][col].y; acc.z += part[k][col].z; acc.w += part[k][col].w; }
+        // partial layout [tap][cout / 4][cin][4] -> TF layout [tap][cin][cout]
+        const int ci = i % F, cg = (i / F) % CG, tap = i / (F * CG);
+        reinterpret_cast<float4 *>(dw)[((size_t)tap * F + ci) * CG + cg] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -582,118 +599,129 @@ __device__ __forceinline__ float block_reduce(float v, float *scratch, bool is_m
     return is_max ? fmaxf(fmaxf(scratch[0], scratch[1]), fmaxf(scratch[2], scratch[3])) : (scratch[0] + scratch[1]) + (scratch[2] + scratch[3]);
 }
 
-__global__ void __launch_bounds__(128) k_heads(const HeadsParams P)
+// A block walks boards blockIdx.x, blockIdx.x + gridDim.x, ...; the weight gradients of the heads are summed in registers over
+// its boards and added to global memory once (one atomic per weight and block instead of one per weight and board).
+__global__ void __launch_bounds__(128) k_heads(const HeadsParams P, int boards)
 {
     __shared__ float h[49][F + 1];
     __shared__ float wp[F][HEAD_OUT];
     __shared__ float out[49][HEAD_OUT];
     __shared__ float dl[49][HEAD_OUT];
     __shared__ float scratch[4];
-    __shared__ float s_val[2];
-    const int board = blockIdx.x, tid = threadIdx.x;
-    const int tile = board >> 1, row0 = (board & 1) * 64;
-    if (board >= P.n) {                                  // the empty half of the last tile: no gradient
-        if (P.train)
-            for (int i = tid; i < CG * 64; i += 128) {
-                const int cg = i / 64, r = i % 64;
-                *reinterpret_cast<float4 *>(P.d_h + (size_t)tile * TB32_TILE_F + (cg * TILE_M + row0 + r) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        return;
-    }
-    for (int i = tid; i < CG * 49; i += 128) {
-        const int cg = i / 49, cell = i % 49;
-        const int r = row0 + 8 + (cell / 7) * 8 + cell % 7;
-        const float4 v = *reinterpret_cast<const float4 *>(P.h32 + (size_t)tile * TB32_TILE_F + (cg * TILE_M + r) * 4);
-        h[cell][cg * 4] = v.x; h[cell][cg * 4 + 1] = v.y; h[cell][cg * 4 + 2] = v.z; h[cell][cg * 4 + 3] = v.w;
-    }
+    const int tid = threadIdx.x;
     for (int i = tid; i < F * HEAD_OUT; i += 128) {
         const int c = i / HEAD_OUT, p = i % HEAD_OUT;
         wp[c][p] = p < POLICY_PLANES ? P.w_policy[c * POLICY_PLANES + p] : P.w_value[c];
     }
-    __syncthreads();
-    for (int o = tid; o < 49 * HEAD_OUT; o += 128) {
-        const int cell = o / HEAD_OUT, p = o % HEAD_OUT;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < F; ++c) acc += h[cell][c] * wp[c][p];
-        out[cell][p] = acc;
-    }
-    __syncthreads();
-    // value head: tanh(sum_cell v[cell] * fc_w[cell] + fc_b)   (model.py:70-76; cells in x-major order like tf.reshape of NHWC)
-    float vterm = tid < 49 ? out[tid][POLICY_PLANES] * P.fc_w[tid] : 0.f;
-    const float pre = block_reduce(vterm, scratch, false) + P.fc_b[0];
-    const float val = tanhf(pre);
-    // policy: softmax cross-entropy with soft labels over the 833 logits (model.py:83-86)
-    float mx = -INFINITY;
-    for (int i = tid; i < AZ_LOGITS; i += 128) mx = fmaxf(mx, out[i / POLICY_PLANES][i % POLICY_PLANES]);
-    mx = block_reduce(mx, scratch, true);
-    float se = 0.f, st = 0.f, stx = 0.f;
-    const float *target = P.policies + (size_t)board * AZ_LOGITS;
-    for (int i = tid; i < AZ_LOGITS; i += 128) {
-        const float x = out[i / POLICY_PLANES][i % POLICY_PLANES] - mx, t = target[i];
-        se += expf(x);
-        st += t;
-        stx += t * x;
-    }
-    se = block_reduce(se, scratch, false);
-    st = block_reduce(st, scratch, false);
-    stx = block_reduce(stx, scratch, false);
-    const float lse = logf(se);
-    const float want = P.values[board];
-    const float inv_n = 1.f / (float)P.n;
-    if (tid == 0) {
-        atomicAdd(P.loss + 0, (double)(st * lse - stx) * (double)inv_n);          // -sum t * (x - lse)
-        atomicAdd(P.loss + 1, (double)((want - val) * (want - val)) * (double)inv_n);
-        if (P.values_out) P.values_out[board] = val;
-    }
-    if (P.logits_out)
-        for (int i = tid; i < AZ_LOGITS; i += 128) P.logits_out[(size_t)board * AZ_LOGITS + i] = out[i / POLICY_PLANES][i % POLICY_PLANES];
-    if (!P.train) return;
-
-    // gradients of the (mean over the batch) losses w.r.t. the head outputs
-    const float dpre = 2.f * (val - want) * inv_n * (1.f - val * val);
-    for (int i = tid; i < AZ_LOGITS; i += 128) {
-        const int cell = i / POLICY_PLANES, p = i % POLICY_PLANES;
-        dl[cell][p] = (expf(out[cell][p] - mx - lse) * st - target[i]) * inv_n;
-    }
-    if (tid < 49) {
-        dl[tid][POLICY_PLANES] = dpre * P.fc_w[tid];
-        atomicAdd(P.g_fc_w + tid, dpre * out[tid][POLICY_PLANES]);
-    }
-    if (tid == 0) atomicAdd(P.g_fc_b, dpre);
-    __syncthreads();
-    // thread = channel: weight gradients of the two 1x1 convs, and the gradient flowing into the tower
-    {
-        const int c = tid;
-        float gw[HEAD_OUT];
+    float gw[HEAD_OUT];                                  // thread = channel: d loss / d (policy | value conv weights of this channel)
 #pragma unroll
-        for (int p = 0; p < HEAD_OUT; ++p) gw[p] = 0.f;
-        for (int cell = 0; cell < 49; ++cell) {
-            const float hv = h[cell][c];
+    for (int p = 0; p < HEAD_OUT; ++p) gw[p] = 0.f;
+    float g_fc = 0.f, g_bias = 0.f;                      // threads 0..48: d loss / d fc_w[tid]; thread 0: d loss / d fc_b
+    double loss_p = 0.0, loss_v = 0.0;
+    const float inv_n = 1.f / (float)P.n;
+
+    for (int board = blockIdx.x; board < boards; board += gridDim.x) {
+        const int tile = board >> 1, row0 = (board & 1) * 64;
+        if (board >= P.n) {                              // the empty half of the last tile: no gradient
+            if (P.train)
+                for (int i = tid; i < CG * 64; i += 128) {
+                    const int cg = i / 64, r = i % 64;
+                    *reinterpret_cast<float4 *>(P.d_h + (size_t)tile * TB32_TILE_F + (cg * TILE_M + row0 + r) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            continue;
+        }
+        __syncthreads();                                 // the previous board's h / dl are no longer read
+        for (int i = tid; i < CG * 49; i += 128) {
+            const int cg = i / 49, cell = i % 49;
+            const int r = row0 + 8 + (cell / 7) * 8 + cell % 7;
+            const float4 v = *reinterpret_cast<const float4 *>(P.h32 + (size_t)tile * TB32_TILE_F + (cg * TILE_M + r) * 4);
+            h[cell][cg * 4] = v.x; h[cell][cg * 4 + 1] = v.y; h[cell][cg * 4 + 2] = v.z; h[cell][cg * 4 + 3] = v.w;
+        }
+        __syncthreads();
+        for (int o = tid; o < 49 * HEAD_OUT; o += 128) {
+            const int cell = o / HEAD_OUT, p = o % HEAD_OUT;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < F; ++c) acc += h[cell][c] * wp[c][p];
+            out[cell][p] = acc;
+        }
+        __syncthreads();
+        // value head: tanh(sum_cell v[cell] * fc_w[cell] + fc_b)   (model.py:70-76; cells in x-major order like tf.reshape of NHWC)
+        const float vterm = tid < 49 ? out[tid][POLICY_PLANES] * P.fc_w[tid] : 0.f;
+        const float pre = block_reduce(vterm, scratch, false) + P.fc_b[0];
+        const float val = tanhf(pre);
+        // policy: softmax cross-entropy with soft labels over the 833 logits (model.py:83-86)
+        float mx = -INFINITY;
+        for (int i = tid; i < AZ_LOGITS; i += 128) mx = fmaxf(mx, out[i / POLICY_PLANES][i % POLICY_PLANES]);
+        mx = block_reduce(mx, scratch, true);
+        float se = 0.f, st = 0.f, stx = 0.f;
+        const float *target = P.policies + (size_t)board * AZ_LOGITS;
+        for (int i = tid; i < AZ_LOGITS; i += 128) {
+            const float x = out[i / POLICY_PLANES][i % POLICY_PLANES] - mx, t = target[i];
+            se += expf(x);
+            st += t;
+            stx += t * x;
+        }
+        se = block_reduce(se, scratch, false);
+        st = block_reduce(st, scratch, false);
+        stx = block_reduce(stx, scratch, false);
+        const float lse = logf(se);
+        const float want = P.values[board];
+        if (tid == 0) {
+            loss_p += (double)(st * lse - stx) * (double)inv_n;                      // -sum t * (x - lse)
+            loss_v += (double)((want - val) * (want - val)) * (double)inv_n;
+            if (P.values_out) P.values_out[board] = val;
+        }
+        if (P.logits_out)
+            for (int i = tid; i < AZ_LOGITS; i += 128) P.logits_out[(size_t)board * AZ_LOGITS + i] = out[i / POLICY_PLANES][i % POLICY_PLANES];
+        if (!P.train) continue;
+
+        // gradients of the (mean over the batch) losses w.r.t. the head outputs
+        const float dpre = 2.f * (val - want) * inv_n * (1.f - val * val);
+        for (int i = tid; i < AZ_LOGITS; i += 128) {
+            const int cell = i / POLICY_PLANES, p = i % POLICY_PLANES;
+            dl[cell][p] = (expf(out[cell][p] - mx - lse) * st - target[i]) * inv_n;
+        }
+        if (tid < 49) {
+            dl[tid][POLICY_PLANES] = dpre * P.fc_w[tid];
+            g_fc += dpre * out[tid][POLICY_PLANES];
+        }
+        if (tid == 0) g_bias += dpre;
+        __syncthreads();
+        for (int cell = 0; cell < 49; ++cell) {          // weight gradients of the two 1x1 convs
+            const float hv = h[cell][tid];
 #pragma unroll
             for (int p = 0; p < HEAD_OUT; ++p) gw[p] += hv * dl[cell][p];
         }
+        __syncthreads();
+        for (int cell = 0; cell < 49; ++cell) {          // the gradient flowing into the tower (reuses h[][])
+            float acc = 0.f;
 #pragma unroll
-        for (int p = 0; p < POLICY_PLANES; ++p) atomicAdd(P.g_policy + c * POLICY_PLANES + p, gw[p]);
-        atomicAdd(P.g_value + c, gw[POLICY_PLANES]);
-    }
-    __syncthreads();
-    for (int cell = 0; cell < 49; ++cell) {              // reuse h[][] for d_h
-        float acc = 0.f;
-#pragma unroll
-        for (int p = 0; p < HEAD_OUT; ++p) acc += dl[cell][p] * wp[tid][p];
-        h[cell][tid] = acc;
-    }
-    __syncthreads();
-    for (int i = tid; i < CG * 64; i += 128) {
-        const int cg = i / 64, r = i % 64;
-        const int x = (r >> 3) - 1, y = r & 7;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r >= 8 && y != 7) {
-            const int cell = x * 7 + y;
-            v = make_float4(h[cell][cg * 4], h[cell][cg * 4 + 1], h[cell][cg * 4 + 2], h[cell][cg * 4 + 3]);
+            for (int p = 0; p < HEAD_OUT; ++p) acc += dl[cell][p] * wp[tid][p];
+            h[cell][tid] = acc;
         }
-        *reinterpret_cast<float4 *>(P.d_h + (size_t)tile * TB32_TILE_F + (cg * TILE_M + row0 + r) * 4) = v;
+        __syncthreads();
+        for (int i = tid; i < CG * 64; i += 128) {
+            const int cg = i / 64, r = i % 64;
+            const int x = (r >> 3) - 1, y = r & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r >= 8 && y != 7) {
+                const int cell = x * 7 + y;
+                v = make_float4(h[cell][cg * 4], h[cell][cg * 4 + 1], h[cell][cg * 4 + 2], h[cell][cg * 4 + 3]);
+            }
+            *reinterpret_cast<float4 *>(P.d_h + (size_t)tile * TB32_TILE_F + (cg * TILE_M + row0 + r) * 4) = v;
+        }
+    }
+    if (tid == 0) {
+        atomicAdd(P.loss + 0, loss_p);
+        atomicAdd(P.loss + 1, loss_v);
+    }
+    if (P.train) {
+#pragma unroll
+        for (int p = 0; p < POLICY_PLANES; ++p) atomicAdd(P.g_policy + tid * POLICY_PLANES + p, gw[p]);
+        atomicAdd(P.g_value + tid, gw[POLICY_PLANES]);
+        if (tid < 49) atomicAdd(P.g_fc_w + tid, g_fc);
+        if (tid == 0) atomicAdd(P.g_fc_b, g_bias);
     }
 }
 
@@ -761,6 +789,8 @@ struct az_trainer {
     int8_t *d_feats = nullptr;
     float *d_pol = nullptr, *d_val = nullptr, *d_logits = nullptr, *d_values_out = nullptr;
     double *h_loss = nullptr;                           // pinned
+    cudaEvent_t ev[2] = {nullptr, nullptr};             // around the kernels of a step (inputs already on the device)
+    float last_step_ms = 0.f;
     bool loaded = false;
     unsigned long long steps = 0, launches = 0;
 
@@ -834,7 +864,7 @@ int forward(az_trainer *t, int n, bool train, bool want_outputs)
     H.g_fc_b = t->grad + t->off_fcb;
     H.n = n;
     H.train = train ? 1 : 0;
-    k_heads<<<2 * tiles, 128, 0, s>>>(H);
+    k_heads<<<std::min(2 * tiles, 2 * t->ctx->sm_count), 128, 0, s>>>(H, 2 * tiles);
     t->launches++;
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
@@ -869,7 +899,7 @@ int backward(az_trainer *t, int n)
         const int ranges = std::min(WG_RANGES, tiles);       // every range owns at least one tile
         WgradParams W{t->act_at(l), t->dz, t->wg_partial, tiles};
         k_wgrad<<<dim3(ranges, 9 / WG_TAPS), WG_THREADS, WG_SMEM, s>>>(W);
-        k_wgrad_reduce<<<LAYER_W / 4 / 256, 256, 0, s>>>(t->wg_partial, t->grad + (size_t)l * LAYER_W, ranges);
+        k_wgrad_reduce<<<LAYER_W / 4 / WGR_COLS, WGR_COLS * WGR_SPLIT, 0, s>>>(t->wg_partial, t->grad + (size_t)l * LAYER_W, ranges);
         t->launches += 3;
         if (l > 0) {
             // data gradient: into d_y for the second conv of a block, ON TOP of the skip gradient in d_h for the first
@@ -937,6 +967,7 @@ extern "C" int az_trainer_create(az_context *ctx, int max_batch, int blocks, az_
     rc |= dev_alloc(&t->d_logits, (size_t)max_batch * AZ_LOGITS);
     rc |= dev_alloc(&t->d_values_out, (size_t)max_batch);
     if (!rc && cudaMallocHost(&t->h_loss, 4 * sizeof(double)) != cudaSuccess) rc = az_fail(AZ_ERR_CUDA, "az_trainer_create: pinned host alloc");
+    if (!rc && (cudaEventCreate(&t->ev[0]) != cudaSuccess || cudaEventCreate(&t->ev[1]) != cudaSuccess)) rc = az_fail(AZ_ERR_CUDA, "az_trainer_create: event");
     if (!rc && (cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM) != cudaSuccess ||
                 cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) != cudaSuccess))
         rc = az_fail(AZ_ERR_CUDA, "az_trainer_create: cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
@@ -953,6 +984,8 @@ extern "C" void az_trainer_destroy(az_trainer *t)
                     t->fsum, t->bsum, t->loss, t->wg_partial, t->d_feats, t->d_pol, t->d_val, t->d_logits, t->d_values_out};
     for (void *p : bufs) cudaFree(p);
     if (t->h_loss) cudaFreeHost(t->h_loss);
+    for (cudaEvent_t e : t->ev)
+        if (e) cudaEventDestroy(e);
     delete t;
 }
 
@@ -1003,14 +1036,17 @@ extern "C" int az_trainer_step(az_trainer *t, const int8_t *features, const floa
     AZ_CUDA(cudaMemsetAsync(t->bsum, 0, L * 2 * F * sizeof(double), s));
     AZ_CUDA(cudaMemsetAsync(t->loss, 0, 4 * sizeof(double), s));
     if ((rc = stage_batch(t, features, policies, values, n))) return rc;
+    AZ_CUDA(cudaEventRecord(t->ev[0], s));
     if ((rc = forward(t, n, true, false))) return rc;
     if ((rc = backward(t, n))) return rc;
     k_sgd<<<592, 256, 0, s>>>(t->theta, t->mom, t->grad, t->count, learning_rate, t->loss + 2);
     t->launches++;
     if ((rc = refresh_images(t))) return rc;
+    AZ_CUDA(cudaEventRecord(t->ev[1], s));
     AZ_CUDA(cudaMemcpyAsync(t->h_loss, t->loss, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
     AZ_CUDA(cudaGetLastError());
+    AZ_CUDA(cudaEventElapsedTime(&t->last_step_ms, t->ev[0], t->ev[1]));
     t->steps++;
     if (losses) { losses[0] = (float)t->h_loss[0]; losses[1] = (float)t->h_loss[1]; losses[2] = (float)t->h_loss[2]; }
     for (int i = 0; i < 3; ++i) AZ_REQUIRE(std::isfinite(t->h_loss[i]), AZ_ERR_STATE, "az_trainer_step: loss term %d is not finite (diverged)", i);
@@ -1071,6 +1107,8 @@ extern "C" int az_trainer_export(az_trainer *t, float *packed, size_t count)
 }
 
 extern "C" unsigned long long az_trainer_launches(const az_trainer *t) { return t ? t->launches : 0; }
+// device time of the last step's kernels (CUDA events on the launching stream; the batch was already in HBM)
+extern "C" float az_trainer_last_step_ms(const az_trainer *t) { return t ? t->last_step_ms : 0.f; }
 
 // Test hook (not in the public header's stable part): copies an internal tensor of the LAST step to the host.
 //   what = "z" / "act": conv output / activation of `layer` as float [n][7][7][F]      (act: layer 0 = input .. layers = tower output)

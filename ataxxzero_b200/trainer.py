@@ -17,6 +17,7 @@ register("az_trainer_step", C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_float, _v
 register("az_trainer_eval", C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp])
 register("az_trainer_export", C.c_int, [_vp, _vp, C.c_size_t])
 register("az_trainer_launches", C.c_ulonglong, [_vp])
+register("az_trainer_last_step_ms", C.c_float, [_vp])
 register("az_trainer_debug_read", C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, _vp, C.c_size_t])
 
 
@@ -90,6 +91,11 @@ class Trainer:
     @property
     def launches(self):
         return int(lib().az_trainer_launches(self._h))
+
+    @property
+    def last_step_ms(self):
+        """Device time of the last step's kernels (CUDA events; minibatch already in HBM)."""
+        return float(lib().az_trainer_last_step_ms(self._h))
 
     def debug_read(self, what, layer=0, n=0):
         f = model.Network.FILTERS

@@ -256,6 +256,8 @@ int az_trainer_eval(az_trainer *trainer, const int8_t *features, const float *po
  * of the file format) */
 int az_trainer_export(az_trainer *trainer, float *packed, size_t count);
 unsigned long long az_trainer_launches(const az_trainer *trainer);
+/* device time of the last step's kernels, CUDA events on the launching stream (the minibatch already in HBM) */
+float az_trainer_last_step_ms(const az_trainer *trainer);
 /* test hook: an internal tensor of the last step ("z", "act", "d_h", "grad_conv", "grad_gamma", "grad_beta", "gamma", "beta",
  * "conv", "moving", "grad_heads"), see az_train.cu */
 int az_trainer_debug_read(az_trainer *trainer, const char *what, int layer, int n, float *out, size_t count);

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(native):
 def test_binding_signatures_cover_header(native):
     from ataxxzero_b200 import _native
     import ataxxzero_b200.rules  # noqa: F401  (registers nothing extra, but must import cleanly)
-    for opt in ("net", "search", "selfplay", "link", "train_data"):
+    for opt in ("net", "search", "selfplay", "link", "train_data", "trainer"):
         try:
             __import__("ataxxzero_b200." + opt)
         except ImportError:

@@ -14,7 +14,10 @@ batch = synthetic_batch(N, 2)
 for _ in range(3):
     tr.train(*batch, learning_rate=1e-3)
 t0 = time.perf_counter(); l0 = tr.launches
+dev_ms = 0.0
 for _ in range(STEPS):
     tr.train(*batch, learning_rate=1e-3)
+    dev_ms += tr.last_step_ms
 dt = (time.perf_counter() - t0) / STEPS
-print("native step %d boards x 12 blocks: %.3f ms/step, %.0f samples/s, %d launches/step" % (N, dt * 1e3, N / dt, (tr.launches - l0) // STEPS))
+print("native step %d boards x 12 blocks: %.3f ms/step end to end (host batch in, losses out), %.3f ms/step on the device, %.0f samples/s, %d launches/step" % (
+    N, dt * 1e3, dev_ms / STEPS, N / dt, (tr.launches - l0) // STEPS))
