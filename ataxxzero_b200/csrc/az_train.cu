@@ -72,6 +72,12 @@ __device__ __forceinline__ bool row_is_real(int r, int &board_in_tile, int &cell
     cell = x * 7 + y;
     return w >= 8 && y != 7;
 }
+// Programmatic dependent launch: every kernel of a step lets its successor start at once (its CTAs move in as this kernel's
+// drain, and run their prologue -- barrier init, TMEM allocation, zero fills, parameter loads) and itself waits for its
+// predecessor's memory before it touches global memory.  No-ops when the launch carries no such dependency.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __host__ __device__ __forceinline__ int tap_shift(int tap) { return (tap / 3 - 1) * 8 + (tap % 3 - 1); }
 __device__ __forceinline__ uint4 load_bf8(const uint8_t *tb16, int tile, int kg, int row)
 {
@@ -127,6 +133,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv(const ConvParams P)
     const int tile = blockIdx.x;
     auto bar = [&](int i) { return sbase + CONV_OFF_BAR + 8 * i; };
     constexpr int B_FULL = 0, B_EMPTY = CONV_STAGES, B_IN = 2 * CONV_STAGES, B_ACC = 2 * CONV_STAGES + 1;
+    pdl_trigger();
 
     for (int i = threadIdx.x; i < KG * 2 * MARGIN; i += CONV_THREADS) {          // zero the margins of every channel group
         const int kg = i / (2 * MARGIN), j = i % (2 * MARGIN);
@@ -143,6 +150,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv(const ConvParams P)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + CONV_OFF_TMEM);
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -277,6 +285,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const WgradParams P)
     const int tap0 = blockIdx.y * WG_TAPS;
     auto bar = [&](int i) { return sbase + WG_OFF_BAR + 8 * i; };
     constexpr int B_FULL = 0, B_EMPTY = WG_STAGES, B_ACC = 2 * WG_STAGES;
+    pdl_trigger();
 
     for (int i = threadIdx.x; i < WG_STAGES * KG * 2 * MARGIN; i += WG_THREADS) {
         const int s = i / (KG * 2 * MARGIN), rest = i % (KG * 2 * MARGIN);
@@ -294,6 +303,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad(const WgradParams P)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + WG_OFF_TMEM);
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -366,6 +376,8 @@ __global__ void __launch_bounds__(WGR_COLS * WGR_SPLIT) k_wgrad_reduce(const flo
     __shared__ float4 part[WGR_SPLIT][WGR_COLS];
     const int col = threadIdx.x % WGR_COLS, quarter = threadIdx.x / WGR_COLS;
     const int i = blockIdx.x * WGR_COLS + col;                    // float4 index
+    pdl_trigger();
+    pdl_wait();
     float4 v[WGR_PER];
 #pragma unroll
     for (int k = 0; k < WGR_PER; ++k) {
@@ -431,6 +443,8 @@ __global__ void __launch_bounds__(128) k_stage_input(const int8_t *__restrict__ 
     int bit, cell;
     const bool real = row_is_real(row, bit, cell);
     const int board = tile * 2 + bit;
+    pdl_trigger();
+    pdl_wait();
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (real && board < n) {
         const char4 f = *reinterpret_cast<const char4 *>(feats + ((size_t)board * 49 + cell) * 4);
@@ -455,6 +469,8 @@ __global__ void __launch_bounds__(128) k_bn_apply(const BnApplyParams P)
 {
     const int kg = blockIdx.x, row = threadIdx.x;
     const double cnt = (double)P.n * 49.0;
+    pdl_trigger();
+    pdl_wait();
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -527,6 +543,8 @@ __device__ __forceinline__ void masked_grad(const BnBwdParams &P, int tile, int 
 __global__ void __launch_bounds__(128) k_bn_bwd_stats(const BnBwdParams P)
 {
     const int kg = blockIdx.x, row = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     float mean[8], rstd[8], acc[16];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mean[i] = P.mean_rstd[kg * 8 + i]; rstd[i] = P.mean_rstd[F + kg * 8 + i]; acc[i] = 0.f; acc[8 + i] = 0.f; }
@@ -543,6 +561,8 @@ __global__ void __launch_bounds__(128) k_bn_bwd_apply(const BnBwdParams P)
 {
     const int kg = blockIdx.x, row = threadIdx.x;
     const float inv = 1.f / ((float)P.n * 49.f);
+    pdl_trigger();
+    pdl_wait();
     float mean[8], rstd[8], sg[8], sgx[8], k[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -609,6 +629,8 @@ __global__ void __launch_bounds__(128) k_heads(const HeadsParams P, int boards)
     __shared__ float dl[49][HEAD_OUT];
     __shared__ float scratch[4];
     const int tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     for (int i = tid; i < F * HEAD_OUT; i += 128) {
         const int c = i / HEAD_OUT, p = i % HEAD_OUT;
         wp[c][p] = p < POLICY_PLANES ? P.w_policy[c * POLICY_PLANES + p] : P.w_value[c];
@@ -734,6 +756,8 @@ __global__ void __launch_bounds__(256) k_sgd(float *__restrict__ theta, float *_
 {
     __shared__ float part[8];
     float sq = 0.f;
+    pdl_trigger();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
         const float w = theta[i];
         const float m = MOMENTUM * mom[i] + (grad[i] + L2_SCALE * w);
@@ -758,6 +782,7 @@ __global__ void __launch_bounds__(256) k_sgd(float *__restrict__ theta, float *_
 __global__ void __launch_bounds__(256) k_images(const float *__restrict__ theta, __nv_bfloat16 *__restrict__ img_f, __nv_bfloat16 *__restrict__ img_b, size_t count)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
     if (idx >= count) return;
     const int co = (int)(idx % F), ci = (int)((idx / F) % F), tap = (int)((idx / (F * F)) % 9);
     const size_t l = idx / LAYER_W;
@@ -765,6 +790,24 @@ __global__ void __launch_bounds__(256) k_images(const float *__restrict__ theta,
     const size_t base = l * (size_t)(LAYER_IMG_BYTES / 2);
     img_f[base + ((size_t)(((ci / 64) * 9 + tap) * PART_KG + (ci % 64) / 8) * F + co) * 8 + ci % 8] = w;
     img_b[base + ((size_t)(((co / 64) * 9 + (8 - tap)) * PART_KG + (co % 64) / 8) * F + ci) * 8 + co % 8] = w;
+}
+
+// launch with the programmatic-stream-serialisation attribute (see pdl_trigger); AZ_TRAIN_PDL=0 launches plainly
+template <typename... KArgs, typename... Args>
+void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    static const bool pdl = !(getenv("AZ_TRAIN_PDL") && atoi(getenv("AZ_TRAIN_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 template <typename T>
@@ -803,7 +846,7 @@ namespace {
 int refresh_images(az_trainer *t)
 {
     const size_t n = (size_t)t->layers * LAYER_W;
-    k_images<<<(unsigned)((n + 255) / 256), 256, 0, t->ctx->stream>>>(t->theta, reinterpret_cast<__nv_bfloat16 *>(t->img_f), reinterpret_cast<__nv_bfloat16 *>(t->img_b), n);
+    launch(k_images, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, t->ctx->stream, t->theta, reinterpret_cast<__nv_bfloat16 *>(t->img_f), reinterpret_cast<__nv_bfloat16 *>(t->img_b), n);
     t->launches++;
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
@@ -824,12 +867,12 @@ int forward(az_trainer *t, int n, bool train, bool want_outputs)
     cudaStream_t s = t->ctx->stream;
     const int tiles = (n + 1) / 2;
     const dim3 ew(KG, std::min(tiles, 64));
-    k_stage_input<<<tiles, 128, 0, s>>>(t->d_feats, t->act_at(0), n);
+    launch(k_stage_input, dim3(tiles), dim3(128), 0, s, t->d_feats, t->act_at(0), n);
     t->launches++;
     for (int l = 0; l < t->layers; ++l) {
         // training: the conv epilogue also adds up the batch statistics of its output
         ConvParams C{t->act_at(l), t->img_f + (size_t)l * LAYER_IMG_BYTES, t->z_at(l), 0, train ? t->fsum + (size_t)l * 2 * F : nullptr, nullptr, nullptr, nullptr, nullptr};
-        k_conv<<<tiles, CONV_THREADS, CONV_SMEM, s>>>(C);
+        launch(k_conv, dim3(tiles), dim3(CONV_THREADS), CONV_SMEM, s, C);
         BnApplyParams B{};
         B.z = t->z_at(l);
         B.sums = t->fsum + (size_t)l * 2 * F;
@@ -843,7 +886,7 @@ int forward(az_trainer *t, int n, bool train, bool want_outputs)
         B.tiles = tiles;
         B.n = n;
         B.use_moving = train ? 0 : 1;
-        k_bn_apply<<<ew, 128, 0, s>>>(B);
+        launch(k_bn_apply, dim3(ew), dim3(128), 0, s, B);
         t->launches += 2;
     }
     HeadsParams H{};
@@ -864,7 +907,7 @@ int forward(az_trainer *t, int n, bool train, bool want_outputs)
     H.g_fc_b = t->grad + t->off_fcb;
     H.n = n;
     H.train = train ? 1 : 0;
-    k_heads<<<std::min(2 * tiles, 2 * t->ctx->sm_count), 128, 0, s>>>(H, 2 * tiles);
+    launch(k_heads, dim3(std::min(2 * tiles, 2 * t->ctx->sm_count)), dim3(128), 0, s, H, 2 * tiles);
     t->launches++;
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
@@ -892,20 +935,20 @@ int backward(az_trainer *t, int n)
         B.tiles = tiles;
         B.n = n;
         if (l == t->layers - 1) {                       // every other layer's sums come out of the data-gradient epilogue above it
-            k_bn_bwd_stats<<<ew, 128, 0, s>>>(B);
+            launch(k_bn_bwd_stats, dim3(ew), dim3(128), 0, s, B);
             t->launches++;
         }
-        k_bn_bwd_apply<<<ew, 128, 0, s>>>(B);
+        launch(k_bn_bwd_apply, dim3(ew), dim3(128), 0, s, B);
         const int ranges = std::min(WG_RANGES, tiles);       // every range owns at least one tile
         WgradParams W{t->act_at(l), t->dz, t->wg_partial, tiles};
-        k_wgrad<<<dim3(ranges, 9 / WG_TAPS), WG_THREADS, WG_SMEM, s>>>(W);
-        k_wgrad_reduce<<<LAYER_W / 4 / WGR_COLS, WGR_COLS * WGR_SPLIT, 0, s>>>(t->wg_partial, t->grad + (size_t)l * LAYER_W, ranges);
+        launch(k_wgrad, dim3(dim3(ranges, 9 / WG_TAPS)), dim3(WG_THREADS), WG_SMEM, s, W);
+        launch(k_wgrad_reduce, dim3(LAYER_W / 4 / WGR_COLS), dim3(WGR_COLS * WGR_SPLIT), 0, s, t->wg_partial, t->grad + (size_t)l * LAYER_W, ranges);
         t->launches += 3;
         if (l > 0) {
             // data gradient: into d_y for the second conv of a block, ON TOP of the skip gradient in d_h for the first
             ConvParams C{t->dz, t->img_b + (size_t)l * LAYER_IMG_BYTES, first ? t->d_h : t->d_y, first ? 1 : 0, nullptr,
                          t->act_at(l), t->z_at(l - 1), t->mean_rstd + (size_t)(l - 1) * 2 * F, t->bsum + (size_t)(l - 1) * 2 * F};
-            k_conv<<<tiles, CONV_THREADS, CONV_SMEM, s>>>(C);
+            launch(k_conv, dim3(tiles), dim3(CONV_THREADS), CONV_SMEM, s, C);
             t->launches++;
         }
     }
@@ -1039,7 +1082,7 @@ extern "C" int az_trainer_step(az_trainer *t, const int8_t *features, const floa
     AZ_CUDA(cudaEventRecord(t->ev[0], s));
     if ((rc = forward(t, n, true, false))) return rc;
     if ((rc = backward(t, n))) return rc;
-    k_sgd<<<592, 256, 0, s>>>(t->theta, t->mom, t->grad, t->count, learning_rate, t->loss + 2);
+    launch(k_sgd, dim3(592), dim3(256), 0, s, t->theta, t->mom, t->grad, t->count, learning_rate, t->loss + 2);
     t->launches++;
     if ((rc = refresh_images(t))) return rc;
     AZ_CUDA(cudaEventRecord(t->ev[1], s));
