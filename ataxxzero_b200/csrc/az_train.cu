@@ -471,22 +471,28 @@ __global__ void __launch_bounds__(128) k_bn_apply(const BnApplyParams P)
     const double cnt = (double)P.n * 49.0;
     pdl_trigger();
     pdl_wait();
+    // per-channel scale / shift: the mean and the E[z^2] - mean^2 subtraction in double, the rest in float
+    const double inv_cnt = 1.0 / cnt;
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = kg * 8 + i;
-        double mean, var;
+        float mean, var;
         if (P.use_moving) { mean = P.moving[c]; var = P.moving[F + c]; }
-        else { mean = P.sums[c] / cnt; var = fmax(P.sums[F + c] / cnt - mean * mean, 0.0); }
-        const double rstd = 1.0 / sqrt(var + (double)AZ_BN_EPS);
-        sc[i] = (float)((double)P.gamma[c] * rstd);
-        sh[i] = (float)((double)P.beta[c] - mean * (double)P.gamma[c] * rstd);
+        else {
+            const double m = P.sums[c] * inv_cnt;
+            mean = (float)m;
+            var = fmaxf((float)(P.sums[F + c] * inv_cnt - m * m), 0.f);
+        }
+        const float rstd = 1.f / sqrtf(var + AZ_BN_EPS);
+        sc[i] = P.gamma[c] * rstd;
+        sh[i] = P.beta[c] - mean * sc[i];
         if (blockIdx.y == 0 && row == i && !P.use_moving) {
-            P.mean_rstd[c] = (float)mean;
-            P.mean_rstd[F + c] = (float)rstd;
+            P.mean_rstd[c] = mean;
+            P.mean_rstd[F + c] = rstd;
             // tf.layers.batch_normalization update ops (fused kernel: the moving variance takes the unbiased estimate)
-            P.moving[c] = BN_DECAY * P.moving[c] + (1.f - BN_DECAY) * (float)mean;
-            P.moving[F + c] = BN_DECAY * P.moving[F + c] + (1.f - BN_DECAY) * (float)(var * cnt / fmax(cnt - 1.0, 1.0));
+            P.moving[c] = BN_DECAY * P.moving[c] + (1.f - BN_DECAY) * mean;
+            P.moving[F + c] = BN_DECAY * P.moving[F + c] + (1.f - BN_DECAY) * (var * (float)(cnt / fmax(cnt - 1.0, 1.0)));
         }
     }
     int bit, cell;
@@ -623,10 +629,10 @@ __device__ __forceinline__ float block_reduce(float v, float *scratch, bool is_m
 // its boards and added to global memory once (one atomic per weight and block instead of one per weight and board).
 __global__ void __launch_bounds__(128) k_heads(const HeadsParams P, int boards)
 {
-    __shared__ float h[49][F + 1];
+    __shared__ __align__(16) float h[49][F + 4];         // rows 16-byte aligned: read four channels at a time
     __shared__ float wp[F][HEAD_OUT];
     __shared__ float out[49][HEAD_OUT];
-    __shared__ float dl[49][HEAD_OUT];
+    __shared__ __align__(8) float dl[49][HEAD_OUT];
     __shared__ float scratch[4];
     const int tid = threadIdx.x;
     pdl_trigger();
@@ -636,8 +642,12 @@ __global__ void __launch_bounds__(128) k_heads(const HeadsParams P, int boards)
         wp[c][p] = p < POLICY_PLANES ? P.w_policy[c * POLICY_PLANES + p] : P.w_value[c];
     }
     float gw[HEAD_OUT];                                  // thread = channel: d loss / d (policy | value conv weights of this channel)
+    float wreg[HEAD_OUT];                                // ... and those weights themselves
 #pragma unroll
-    for (int p = 0; p < HEAD_OUT; ++p) gw[p] = 0.f;
+    for (int p = 0; p < HEAD_OUT; ++p) {
+        gw[p] = 0.f;
+        wreg[p] = p < POLICY_PLANES ? P.w_policy[tid * POLICY_PLANES + p] : P.w_value[tid];
+    }
     float g_fc = 0.f, g_bias = 0.f;                      // threads 0..48: d loss / d fc_w[tid]; thread 0: d loss / d fc_b
     double loss_p = 0.0, loss_v = 0.0;
     const float inv_n = 1.f / (float)P.n;
@@ -660,12 +670,20 @@ __global__ void __launch_bounds__(128) k_heads(const HeadsParams P, int boards)
             h[cell][cg * 4] = v.x; h[cell][cg * 4 + 1] = v.y; h[cell][cg * 4 + 2] = v.z; h[cell][cg * 4 + 3] = v.w;
         }
         __syncthreads();
-        for (int o = tid; o < 49 * HEAD_OUT; o += 128) {
-            const int cell = o / HEAD_OUT, p = o % HEAD_OUT;
-            float acc = 0.f;
-#pragma unroll 8
-            for (int c = 0; c < F; ++c) acc += h[cell][c] * wp[c][p];
-            out[cell][p] = acc;
+        if (tid < 7 * HEAD_OUT) {                        // thread = (row of 7 cells, output plane): 7 dot products over the channels
+            const int p = tid % HEAD_OUT, c0 = tid / HEAD_OUT * 7;
+            float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+            for (int c = 0; c < F; c += 4) {
+                const float w0 = wp[c][p], w1 = wp[c + 1][p], w2 = wp[c + 2][p], w3 = wp[c + 3][p];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const float4 hv = *reinterpret_cast<const float4 *>(&h[c0 + j][c]);
+                    acc[j] += hv.x * w0 + hv.y * w1 + hv.z * w2 + hv.w * w3;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 7; ++j) out[c0 + j][p] = acc[j];
         }
         __syncthreads();
         // value head: tanh(sum_cell v[cell] * fc_w[cell] + fc_b)   (model.py:70-76; cells in x-major order like tf.reshape of NHWC)
@@ -710,16 +728,18 @@ __global__ void __launch_bounds__(128) k_heads(const HeadsParams P, int boards)
         }
         if (tid == 0) g_bias += dpre;
         __syncthreads();
-        for (int cell = 0; cell < 49; ++cell) {          // weight gradients of the two 1x1 convs
+        // thread = channel: weight gradients of the two 1x1 convs, and the gradient flowing into the tower (which replaces
+        // this thread's own column of h[][])
+        for (int cell = 0; cell < 49; ++cell) {
             const float hv = h[cell][tid];
-#pragma unroll
-            for (int p = 0; p < HEAD_OUT; ++p) gw[p] += hv * dl[cell][p];
-        }
-        __syncthreads();
-        for (int cell = 0; cell < 49; ++cell) {          // the gradient flowing into the tower (reuses h[][])
             float acc = 0.f;
 #pragma unroll
-            for (int p = 0; p < HEAD_OUT; ++p) acc += dl[cell][p] * wp[tid][p];
+            for (int p = 0; p < HEAD_OUT; p += 2) {
+                const float2 d = *reinterpret_cast<const float2 *>(&dl[cell][p]);
+                gw[p] += hv * d.x;
+                gw[p + 1] += hv * d.y;
+                acc += d.x * wreg[p] + d.y * wreg[p + 1];
+            }
             h[cell][tid] = acc;
         }
         __syncthreads();
@@ -834,6 +854,7 @@ struct az_trainer {
     double *h_loss = nullptr;                           // pinned
     cudaEvent_t ev[2] = {nullptr, nullptr};             // around the kernels of a step (inputs already on the device)
     float last_step_ms = 0.f;
+    int ew_chunks = 64;                                 // blocks per channel group in the elementwise kernels
     bool loaded = false;
     unsigned long long steps = 0, launches = 0;
 
@@ -866,7 +887,7 @@ int forward(az_trainer *t, int n, bool train, bool want_outputs)
 {
     cudaStream_t s = t->ctx->stream;
     const int tiles = (n + 1) / 2;
-    const dim3 ew(KG, std::min(tiles, 64));
+    const dim3 ew(KG, std::min(tiles, t->ew_chunks));
     launch(k_stage_input, dim3(tiles), dim3(128), 0, s, t->d_feats, t->act_at(0), n);
     t->launches++;
     for (int l = 0; l < t->layers; ++l) {
@@ -917,7 +938,7 @@ int backward(az_trainer *t, int n)
 {
     cudaStream_t s = t->ctx->stream;
     const int tiles = (n + 1) / 2;
-    const dim3 ew(KG, std::min(tiles, 64));
+    const dim3 ew(KG, std::min(tiles, t->ew_chunks));
     for (int l = t->layers - 1; l >= 0; --l) {
         const bool second = l > 0 && (l & 1) == 0;      // second conv of a block: its output gradient is the block's (d_h)
         const bool first = (l & 1) == 1;
@@ -978,6 +999,7 @@ extern "C" int az_trainer_create(az_context *ctx, int max_batch, int blocks, az_
     t->max_tiles = (max_batch + 1) / 2;
     t->blocks = blocks;
     t->layers = 1 + 2 * blocks;
+    if (getenv("AZ_TRAIN_EW_CHUNKS")) t->ew_chunks = std::max(1, atoi(getenv("AZ_TRAIN_EW_CHUNKS")));
     const size_t L = (size_t)t->layers, T = (size_t)t->max_tiles;
     t->off_gamma = L * LAYER_W;
     t->off_beta = t->off_gamma + L * F;
