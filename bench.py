@@ -548,6 +548,34 @@ def run_ours(args):
                        "tree_ms_per_tick": cd["tree_seconds"] / max(cd.get("timed_ticks", 0), 1) * 1e3,
                        "net_ms_per_tick": cd["net_seconds"] / max(cd.get("timed_ticks", 0), 1) * 1e3}
 
+    # ---- the reference's optimisation step (train.py defaults: minibatch 512, 128 filters x 12 blocks) ----
+    train_step = {}
+    if rank == 0 and world == 1 and not args.no_single_tree:
+        from ataxxzero_b200 import trainer as aztrainer
+        rng = np.random.default_rng(11)
+        feats = np.zeros((512, 7, 7, 4), np.int8)
+        feats[..., 0] = 1
+        who = rng.integers(0, 3, size=(512, 7, 7))
+        feats[..., 1], feats[..., 2] = who == 1, who == 2
+        pol = rng.random((512, 7, 7, 17)).astype(np.float32) ** 8
+        pol /= pol.reshape(512, -1).sum(1).reshape(512, 1, 1, 1)
+        val = rng.choice([-1.0, 1.0], size=(512, 1)).astype(np.float32)
+        tr = aztrainer.Trainer(ctx, model.Network.random_init(seed=1), max_batch=512)
+        for _ in range(3):
+            tr.train(feats, pol, val, learning_rate=1e-3)
+        l0, dev_ms, t0 = tr.launches, 0.0, time.perf_counter()
+        for _ in range(30):
+            tr.train(feats, pol, val, learning_rate=1e-3)
+            dev_ms += tr.last_step_ms
+        wall = (time.perf_counter() - t0) / 30
+        n_launch = (tr.launches - l0) // 30
+        tr.close()
+        flop = 3 * 512 * FLOP_PER_EVAL                   # forward + data gradient + weight gradient (algorithmic)
+        train_step = {"minibatch": 512, "network": "128 filters x 12 blocks", "ms_per_step_e2e": wall * 1e3, "ms_per_step_device": dev_ms / 30,
+                      "samples_per_s_e2e": 512 / wall, "gpu_launches_per_step": n_launch,
+                      "tensor_tflops": flop / (dev_ms / 30 * 1e-3) / 1e12, "frac_of_bf16_peak": flop / (dev_ms / 30 * 1e-3) / 1e12 / peak,
+                      "note": "host minibatch in, losses out per step (e2e); device = CUDA events around the step's kernels; operands bf16, fp32 accumulate / master weights"}
+
     # ---- BASELINE configs[0]: uniformly random play, 2000 games, on the device (records copied back to the host) ----
     start = rules.set_board(rules.OPEN_FEN)
     rules.random_playouts(ctx, start, 2000, 400, seed=1)
@@ -589,7 +617,7 @@ def run_ours(args):
             "e2e": e2e, "roofline": roofline, "clocks": clocks, "gpu_launches": int(d["kernel_launches"]),
             "extra": {"leaf_evals_per_s": evals / (ms * 1e-3), "mcts_steps_per_s": steps / (ms * 1e-3),
                       "evals_per_position": evals / max(positions, 1), "max_depth": s1["max_depth"], "perft": perft,
-                      "single_tree": single, "config3_256x400": config3, "random_play": random_play}}
+                      "single_tree": single, "config3_256x400": config3, "random_play": random_play, "train_step": train_step}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pool.close()
         try:
