@@ -96,6 +96,16 @@ gw_ref = (net.fc_w.grad - lam * net.fc_w).detach().reshape(49).cpu().numpy()
 gb_ref = (net.fc_b.grad - lam * net.fc_b).detach().cpu().numpy()
 print("heads: grad_policy rel %.2e  grad_value rel %.2e  grad_fc_w rel %.2e  grad_fc_b rel %.2e" % (
     rel(gh[:128 * 17].reshape(128, 17), gp_ref), rel(gh[128 * 17:128 * 18], gv_ref), rel(gh[128 * 18:128 * 18 + 49], gw_ref), rel(gh[-1:], gb_ref)))
+# how large is bf16 operand rounding by itself?  the SAME PyTorch graph under bf16 autocast against its own fp32 gradients
+import copy
+net16 = copy.deepcopy(net)
+for p_ in net16.parameters():
+    p_.grad = None
+with torch.autocast("cuda", dtype=torch.bfloat16):
+    p16, v16, r16 = ref.loss_terms(net16, x, pol, val)
+(p16.float() + v16.float() + r16.float()).backward()
+print("PyTorch bf16 autocast vs its own fp32 gradients (operand rounding alone): " + "  ".join(
+    "layer %d %.2e" % (l, rel(net16.convs[l].weight.grad.float().cpu().numpy(), net.convs[l].weight.grad.cpu().numpy())) for l in reversed(range(L))))
 opt.step()
 for l in (0, 1, L - 1):
     w_ours = tr.debug_read("conv", l)
