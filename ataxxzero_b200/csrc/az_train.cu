@@ -88,18 +88,27 @@ __device__ __forceinline__ uint4 load_bf8(const uint8_t *tb16, int tile, int kg,
 // k_conv: forward convolution / data gradient of one layer, one CTA per tile
 // ------------------------------------------------------------------------------------------
 constexpr int CONV_STAGES = 4;
-constexpr int CONV_OFF_RING = ACT_BYTES;
-constexpr int CONV_OFF_BAR = CONV_OFF_RING + CONV_STAGES * STAGE_BYTES;
 constexpr int CONV_BARS = 2 * CONV_STAGES + 2;         // full[4], empty[4], input, accumulator
-constexpr int CONV_OFF_TMEM = CONV_OFF_BAR + CONV_BARS * 8;
-constexpr int CONV_SMEM = CONV_OFF_TMEM + 16;
-constexpr int CONV_THREADS = 192;                      // warp 0 copies, warp 1 issues MMAs, warps 2..5 epilogue
-static_assert(2 * (CONV_SMEM + 1024) <= 228 * 1024, "two conv CTAs per SM");
+// TILES tiles per CTA share every weight stage: 1 -> two CTAs per SM; 2 -> one CTA per SM whose 16-KiB stages each feed 8 MMAs
+// (an SM takes in ~45 B/clk, so with one tile per CTA the 288-KiB weight image, not the tensor pipe, paces the kernel)
+template <int TILES>
+struct ConvCfg {
+    static constexpr int OFF_RING = TILES * ACT_BYTES;
+    static constexpr int OFF_BAR = OFF_RING + CONV_STAGES * STAGE_BYTES;
+    static constexpr int OFF_TMEM = OFF_BAR + CONV_BARS * 8;
+    static constexpr int SMEM = OFF_TMEM + 16;
+    static constexpr int THREADS = 64 + TILES * 128;   // warp 0 copies, warp 1 issues MMAs, 4 epilogue warps per tile
+    static constexpr int CTAS_PER_SM = TILES == 1 ? 2 : 1;
+    static constexpr uint32_t TMEM_COLS = TILES * 128;
+};
+static_assert(2 * (ConvCfg<1>::SMEM + 1024) <= 228 * 1024, "two 1-tile conv CTAs per SM");
+static_assert(ConvCfg<2>::SMEM + 1024 <= 227 * 1024, "one 2-tile conv CTA per SM");
 
 struct ConvParams {
     const uint8_t *in;       // TB16
     const uint8_t *w;        // weight image of the layer
     float *out;              // TB32
+    int tiles;               // tiles of the batch (a CTA of the 2-tile variant may own a tile beyond the end)
     int accumulate;          // 1: out += result (the skip connection's gradient is already there)
     double *stats;           // optional [2][F]: per-channel sum / sum of squares of the result are added (batch-norm statistics)
     // data-gradient launches: the result is the gradient w.r.t. the OUTPUT of the layer below; the first pass of that
@@ -125,18 +134,20 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane)
     return v[0];
 }
 
-__global__ void __launch_bounds__(CONV_THREADS, 2) k_conv(const ConvParams P)
+template <int TILES>
+__global__ void __launch_bounds__(ConvCfg<TILES>::THREADS, ConvCfg<TILES>::CTAS_PER_SM) k_conv(const ConvParams P)
 {
+    using C = ConvCfg<TILES>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    auto bar = [&](int i) { return sbase + CONV_OFF_BAR + 8 * i; };
+    const int tile0 = blockIdx.x * TILES;
+    auto bar = [&](int i) { return sbase + C::OFF_BAR + 8 * i; };
     constexpr int B_FULL = 0, B_EMPTY = CONV_STAGES, B_IN = 2 * CONV_STAGES, B_ACC = 2 * CONV_STAGES + 1;
     pdl_trigger();
 
-    for (int i = threadIdx.x; i < KG * 2 * MARGIN; i += CONV_THREADS) {          // zero the margins of every channel group
-        const int kg = i / (2 * MARGIN), j = i % (2 * MARGIN);
+    for (int i = threadIdx.x; i < TILES * KG * 2 * MARGIN; i += C::THREADS) {    // zero the margins of every channel group
+        const int kg = i / (2 * MARGIN), j = i % (2 * MARGIN);                   // (kg runs over the tiles' groups: ACT_BYTES = KG * ACT_LBO)
         const int row = j < MARGIN ? j : TILE_M + j;
         *reinterpret_cast<uint4 *>(smem + kg * ACT_LBO + row * ROW_BYTES) = make_uint4(0, 0, 0, 0);
     }
@@ -144,24 +155,29 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv(const ConvParams P)
         for (int i = 0; i < CONV_BARS; ++i) mbar_init(bar(i), 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(sbase + CONV_OFF_TMEM, 128);
+    if (warp == 1) tmem_alloc(sbase + C::OFF_TMEM, C::TMEM_COLS);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + CONV_OFF_TMEM);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + C::OFF_TMEM);
     pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(bar(B_IN), TB16_TILE);
-            const uint8_t *src = P.in + (size_t)tile * TB16_TILE;
-            for (int kg = 0; kg < KG; ++kg) bulk_g2s(sbase + kg * ACT_LBO + MARGIN * ROW_BYTES, src + kg * SLICE_BYTES, SLICE_BYTES, bar(B_IN));
+            int have = 0;
+            for (int t = 0; t < TILES; ++t) have += tile0 + t < P.tiles;
+            mbar_expect_tx(bar(B_IN), have * TB16_TILE);
+            for (int t = 0; t < have; ++t) {
+                const uint8_t *src = P.in + (size_t)(tile0 + t) * TB16_TILE;
+                for (int kg = 0; kg < KG; ++kg)
+                    bulk_g2s(sbase + t * ACT_BYTES + kg * ACT_LBO + MARGIN * ROW_BYTES, src + kg * SLICE_BYTES, SLICE_BYTES, bar(B_IN));
+            }
             for (int c = 0; c < CHUNKS; ++c) {
                 const int s = c % CONV_STAGES;
                 mbar_wait(bar(B_EMPTY + s), ((c / CONV_STAGES) & 1) ^ 1);
                 mbar_expect_tx(bar(B_FULL + s), STAGE_BYTES);
-                bulk_g2s(sbase + CONV_OFF_RING + s * STAGE_BYTES, P.w + (size_t)c * STAGE_BYTES, STAGE_BYTES, bar(B_FULL + s));
+                bulk_g2s(sbase + C::OFF_RING + s * STAGE_BYTES, P.w + (size_t)c * STAGE_BYTES, STAGE_BYTES, bar(B_FULL + s));
             }
         }
     } else if (warp == 1) {
@@ -173,44 +189,57 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv(const ConvParams P)
                 const int s = c % CONV_STAGES, part = c / 9, tap = c % 9;
                 mbar_wait(bar(B_FULL + s), (c / CONV_STAGES) & 1);
                 tc_fence_after();
-                const uint32_t a0 = sbase + part * PART_KG * ACT_LBO + (MARGIN + tap_shift(tap)) * ROW_BYTES;
-                const uint32_t b0 = sbase + CONV_OFF_RING + s * STAGE_BYTES;
+                const uint32_t b0 = sbase + C::OFF_RING + s * STAGE_BYTES;
 #pragma unroll
-                for (int j = 0; j < PART_KG / 2; ++j)
-                    umma(tmem_base, make_desc(a0 + 2 * j * ACT_LBO, ACT_LBO, 128), make_desc(b0 + 2 * j * W_LBO, W_LBO, 128), IDESC, (uint32_t)((c | j) != 0));
+                for (int t = 0; t < TILES; ++t) {       // a tile beyond the end multiplies stale shared memory into an accumulator nobody reads
+                    const uint32_t a0 = sbase + t * ACT_BYTES + part * PART_KG * ACT_LBO + (MARGIN + tap_shift(tap)) * ROW_BYTES;
+#pragma unroll
+                    for (int j = 0; j < PART_KG / 2; ++j)
+                        umma(tmem_base + t * 128, make_desc(a0 + 2 * j * ACT_LBO, ACT_LBO, 128), make_desc(b0 + 2 * j * W_LBO, W_LBO, 128), IDESC,
+                             (uint32_t)((c | j) != 0));
+                }
                 umma_commit(bar(B_EMPTY + s));
             }
             umma_commit(bar(B_ACC));
         }
     } else {
+        const int et = (warp - 2) >> 2;                 // tile of this epilogue warp
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
         const int r = quad * 32 + lane;
+        const int tile = tile0 + et;
+        const bool have_tile = tile < P.tiles;
         int bit, cell;
         const bool real = row_is_real(r, bit, cell);
         float *dst = P.out + (size_t)tile * TB32_TILE_F + r * 4;
         mbar_wait(bar(B_ACC), 0);
         tc_fence_after();
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        float *part = reinterpret_cast<float *>(smem);  // [4 warps][2][F] column sums; the staged input is dead by now
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + et * 128;
+        float *part = reinterpret_cast<float *>(smem);  // [TILES * 4 warps][2][F] column sums; the staged input is dead by now
         const bool sums = P.stats || P.below_act;
+        const int pw = et * 4 + quad;
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
-            uint32_t a[32];
-            tmem_ld32(lane_addr + q * 32, a);
-            tmem_wait_ld();
             float v[32];
+            if (have_tile) {
+                uint32_t a[32];
+                tmem_ld32(lane_addr + q * 32, a);
+                tmem_wait_ld();
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                float4 o = real ? make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 *p = reinterpret_cast<float4 *>(dst + (q * 8 + g) * TILE_M * 4);
-                if (P.accumulate) { const float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                *p = o;
-                v[4 * g] = o.x; v[4 * g + 1] = o.y; v[4 * g + 2] = o.z; v[4 * g + 3] = o.w;
+                for (int g = 0; g < 8; ++g) {
+                    float4 o = real ? make_float4(__uint_as_float(a[4 * g]), __uint_as_float(a[4 * g + 1]), __uint_as_float(a[4 * g + 2]), __uint_as_float(a[4 * g + 3]))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 *p = reinterpret_cast<float4 *>(dst + (q * 8 + g) * TILE_M * 4);
+                    if (P.accumulate) { const float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                    *p = o;
+                    v[4 * g] = o.x; v[4 * g + 1] = o.y; v[4 * g + 2] = o.z; v[4 * g + 3] = o.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
             }
             if (sums) {
                 float w[32];
-                if (P.stats) {
+                if (P.stats || !have_tile) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
                 } else {
@@ -236,29 +265,35 @@ __global__ void __launch_bounds__(CONV_THREADS, 2) k_conv(const ConvParams P)
                         }
                     }
                 }
-                part[(quad * 2 + 0) * F + q * 32 + lane] = warp_column_sums(v, lane);
-                part[(quad * 2 + 1) * F + q * 32 + lane] = warp_column_sums(w, lane);
+                part[(pw * 2 + 0) * F + q * 32 + lane] = warp_column_sums(v, lane);
+                part[(pw * 2 + 1) * F + q * 32 + lane] = warp_column_sums(w, lane);
             }
         }
         if (sums) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            double *dst_sums = P.stats ? P.stats : P.below_sums;
-            const int c = (warp - 2) * 32 + lane;
+            if (TILES == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) {
+                double *dst_sums = P.stats ? P.stats : P.below_sums;
+                const int c = (warp - 2) * 32 + lane;
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-                atomicAdd(dst_sums + k * F + c, (double)part[(0 * 2 + k) * F + c] + (double)part[(1 * 2 + k) * F + c] + (double)part[(2 * 2 + k) * F + c] +
-                                                    (double)part[(3 * 2 + k) * F + c]);
+                for (int k = 0; k < 2; ++k) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int w8 = 0; w8 < TILES * 4; ++w8) s += (double)part[(w8 * 2 + k) * F + c];
+                    atomicAdd(dst_sums + k * F + c, s);
+                }
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 128);
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------
 // k_wgrad: weight gradient of one layer.  grid = (row ranges, 3 tap groups)
 // ------------------------------------------------------------------------------------------
-constexpr int WG_STAGES = 2;
+constexpr int WG_STAGES = 3;
 constexpr int WG_STAGE_BYTES = ACT_BYTES + TB16_TILE;                // staged input tile (with margins) + dz tile
 constexpr int WG_OFF_BAR = WG_STAGES * WG_STAGE_BYTES;
 constexpr int WG_BARS = 2 * WG_STAGES + 1;
@@ -855,6 +890,7 @@ struct az_trainer {
     cudaEvent_t ev[2] = {nullptr, nullptr};             // around the kernels of a step (inputs already on the device)
     float last_step_ms = 0.f;
     int ew_chunks = 64;                                 // blocks per channel group in the elementwise kernels
+    int conv_tiles = 0;                                 // 0: by batch size
     bool loaded = false;
     unsigned long long steps = 0, launches = 0;
 
@@ -863,6 +899,14 @@ struct az_trainer {
 };
 
 namespace {
+
+// batches that fill the GPU more than once with one tile per CTA run the 2-tile variant (AZ_TRAIN_CONV_TILES=1|2 forces one)
+void launch_conv(az_trainer *t, int tiles, cudaStream_t s, const ConvParams &C)
+{
+    const int variant = t->conv_tiles ? t->conv_tiles : (tiles > t->ctx->sm_count ? 2 : 1);
+    if (variant == 2) launch(k_conv<2>, dim3((tiles + 1) / 2), dim3(ConvCfg<2>::THREADS), ConvCfg<2>::SMEM, s, C);
+    else launch(k_conv<1>, dim3(tiles), dim3(ConvCfg<1>::THREADS), ConvCfg<1>::SMEM, s, C);
+}
 
 int refresh_images(az_trainer *t)
 {
@@ -892,8 +936,8 @@ int forward(az_trainer *t, int n, bool train, bool want_outputs)
     t->launches++;
     for (int l = 0; l < t->layers; ++l) {
         // training: the conv epilogue also adds up the batch statistics of its output
-        ConvParams C{t->act_at(l), t->img_f + (size_t)l * LAYER_IMG_BYTES, t->z_at(l), 0, train ? t->fsum + (size_t)l * 2 * F : nullptr, nullptr, nullptr, nullptr, nullptr};
-        launch(k_conv, dim3(tiles), dim3(CONV_THREADS), CONV_SMEM, s, C);
+        ConvParams C{t->act_at(l), t->img_f + (size_t)l * LAYER_IMG_BYTES, t->z_at(l), tiles, 0, train ? t->fsum + (size_t)l * 2 * F : nullptr, nullptr, nullptr, nullptr, nullptr};
+        launch_conv(t, tiles, s, C);
         BnApplyParams B{};
         B.z = t->z_at(l);
         B.sums = t->fsum + (size_t)l * 2 * F;
@@ -967,9 +1011,9 @@ int backward(az_trainer *t, int n)
         t->launches += 3;
         if (l > 0) {
             // data gradient: into d_y for the second conv of a block, ON TOP of the skip gradient in d_h for the first
-            ConvParams C{t->dz, t->img_b + (size_t)l * LAYER_IMG_BYTES, first ? t->d_h : t->d_y, first ? 1 : 0, nullptr,
+            ConvParams C{t->dz, t->img_b + (size_t)l * LAYER_IMG_BYTES, first ? t->d_h : t->d_y, tiles, first ? 1 : 0, nullptr,
                          t->act_at(l), t->z_at(l - 1), t->mean_rstd + (size_t)(l - 1) * 2 * F, t->bsum + (size_t)(l - 1) * 2 * F};
-            launch(k_conv, dim3(tiles), dim3(CONV_THREADS), CONV_SMEM, s, C);
+            launch_conv(t, tiles, s, C);
             t->launches++;
         }
     }
@@ -999,6 +1043,7 @@ extern "C" int az_trainer_create(az_context *ctx, int max_batch, int blocks, az_
     t->max_tiles = (max_batch + 1) / 2;
     t->blocks = blocks;
     t->layers = 1 + 2 * blocks;
+    if (getenv("AZ_TRAIN_CONV_TILES")) t->conv_tiles = atoi(getenv("AZ_TRAIN_CONV_TILES")) == 2 ? 2 : 1;
     if (getenv("AZ_TRAIN_EW_CHUNKS")) t->ew_chunks = std::max(1, atoi(getenv("AZ_TRAIN_EW_CHUNKS")));
     const size_t L = (size_t)t->layers, T = (size_t)t->max_tiles;
     t->off_gamma = L * LAYER_W;
@@ -1033,7 +1078,8 @@ extern "C" int az_trainer_create(az_context *ctx, int max_batch, int blocks, az_
     rc |= dev_alloc(&t->d_values_out, (size_t)max_batch);
     if (!rc && cudaMallocHost(&t->h_loss, 4 * sizeof(double)) != cudaSuccess) rc = az_fail(AZ_ERR_CUDA, "az_trainer_create: pinned host alloc");
     if (!rc && (cudaEventCreate(&t->ev[0]) != cudaSuccess || cudaEventCreate(&t->ev[1]) != cudaSuccess)) rc = az_fail(AZ_ERR_CUDA, "az_trainer_create: event");
-    if (!rc && (cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM) != cudaSuccess ||
+    if (!rc && (cudaFuncSetAttribute(k_conv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<1>::SMEM) != cudaSuccess ||
+                cudaFuncSetAttribute(k_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<2>::SMEM) != cudaSuccess ||
                 cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) != cudaSuccess))
         rc = az_fail(AZ_ERR_CUDA, "az_trainer_create: cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc) { az_trainer_destroy(t); return rc; }
