@@ -411,3 +411,51 @@ long tm_spec_sim(const char *fen, int visits, int evaluator, int top_k, long *ev
     tm_free(t);
     return now;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Design study: how often does a simulation walk THROUGH the node the previous simulation created?  (A pool that backs a
+ * leaf's value up at once but computes its priors off the critical path would have to hold such a simulation back for a
+ * tick.)  `plays` > 0: after `visits` root visits play the most visited move and search on, like self-play with tree reuse.
+ * Returns simulations counted; *through_out = those that passed through the previous simulation's new node.
+ * ------------------------------------------------------------------------------------------------ */
+long tm_revisit_sim(const char *fen, int visits, int evaluator, int plays, long *through_out)
+{
+    ao_position p;
+    if (ao_set_board(&p, fen) != 0) return -1;
+    ao_eval_fn fn = evaluator == 1 ? ao_uniform_eval : evaluator == 2 ? flat_eval : ao_probe_eval;
+    tm_tree *t = (tm_tree *)tm_new(&p, fn, NULL, 0);
+    long sims = 0, through = 0;
+    tm_node *last = NULL;
+    for (int round = 0; round <= plays; round++) {
+        while (t->root->N < visits) {
+            tm_node *node = t->root;
+            int sel, hit = 0;
+            for (;;) {
+                if (node == last) hit = 1;
+                sel = tm_select(t, node);
+                if (sel < 0 || sel <= -2) break;
+                node = node->ent[sel].child;
+            }
+            const int before = t->root->N;
+            tm_node *parent = node;
+            const int k_before = parent->k;
+            tm_step(t);
+            if (t->root->N == before) goto done;                 /* terminal root */
+            sims++;
+            through += hit;
+            last = (sel <= -2 && parent->k > k_before && !parent->ent[parent->k - 1].child->terminal) ? parent->ent[parent->k - 1].child : NULL;
+        }
+        if (round == plays) break;
+        int best = -1;
+        for (int e = 0; e < t->root->k; e++)
+            if (best < 0 || t->root->ent[e].n > t->root->ent[best].n) best = e;
+        if (best < 0) break;
+        const int idx = t->root->ent[best].idx;
+        last = NULL;
+        if (tm_play(t, t->root->from[idx], t->root->to[idx]) != 0) break;
+    }
+done:
+    if (through_out) *through_out = through;
+    tm_free(t);
+    return sims;
+}
