@@ -3,8 +3,10 @@
 Every optimisation step runs in libataxxzero.so (csrc/az_train.cu, bound by ataxxzero_b200/trainer.py): the network of
 model.py (conv3x3 + batch-norm + ReLU tower, residual blocks, policy / value heads) forward and backward on the tensor
 cores, the reference's loss -- mean soft-label cross-entropy over the 833 logits + mean squared value error + 1e-4 * sum
-of l2_loss over every trainable variable -- and ``MomentumOptimizer(lr, 0.9)``.  Minibatches come from
-``az_samples_extract`` (train_data.minibatch) instead of one Python-built sample at a time (train.py:121-128).  There is
+of l2_loss over every trainable variable -- and ``MomentumOptimizer(lr, 0.9)``.  The games are packed once and kept on the
+device; every step draws its samples' descriptions in one NumPy call (train_data.draw_arrays) and ``az_trainer_step_picks`` runs
+sample extraction (the ``az_samples_extract`` kernel) and the step back to back, instead of one Python-built sample at a time
+(train.py:121-128).  There is
 no PyTorch and no CPU path here: without a B200 the script stops (tests/torch_train_reference.py holds the fp32 PyTorch
 restatement the step is checked against).
 Like the reference, only conv / FC weights and the batch-norm MOVING statistics are written to the ``.npy``: the learned
@@ -62,7 +64,10 @@ def main(argv=None):
     net = trainer.Trainer(ctx, network, max_batch=max(args.minibatch_size, 2))
     rng = random.Random(123456789)
     val_batch = make_minibatch_fn(test_entries or train_entries, ctx)(min(2048, 64 * max(len(test_entries), 1)), rng)
-    train_batch = make_minibatch_fn(train_entries or test_entries, ctx)
+    # the training games live on the device for the whole run; a step ships only the description of its samples
+    train_games = train_data.pack_entries(train_entries or test_entries)
+    net.set_games(train_games)
+    np_rng = np.random.default_rng(rng.getrandbits(63))
     print("Model dimensions: %i filters, %i blocks, %i parameters." % (network.filters, network.blocks, network.total_parameters))
     print("=== BEGINNING TRAINING ===")
     history = []
@@ -75,7 +80,7 @@ def main(argv=None):
     for step in range(args.steps):
         if step % 100 == 0:
             report(step)
-        net.train(*train_batch(args.minibatch_size, rng), learning_rate=args.learning_rate)
+        net.train_picks(*train_data.draw_arrays(train_games, args.minibatch_size, np_rng), learning_rate=args.learning_rate)
     p_loss, v_loss = net.losses(*val_batch)
     history.append((p_loss, v_loss))
     azmodel.save_model(net.network(), args.new_path)

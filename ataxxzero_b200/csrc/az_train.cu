@@ -884,6 +884,10 @@ struct az_trainer {
     uint8_t *img_f = nullptr, *img_b = nullptr, *act = nullptr, *dz = nullptr;
     float *z = nullptr, *h32 = nullptr, *d_h = nullptr, *d_y = nullptr, *wg_partial = nullptr;
     double *fsum = nullptr, *bsum = nullptr, *loss = nullptr;
+    uint32_t *d_plies = nullptr;                        // resident ply table (az_trainer_set_games)
+    std::vector<uint32_t> h_plies;                      // host copy: the picks of every step are validated against it
+    unsigned long long *d_offsets = nullptr;
+    uint32_t *d_meta = nullptr;
     int8_t *d_feats = nullptr;
     float *d_pol = nullptr, *d_val = nullptr, *d_logits = nullptr, *d_values_out = nullptr;
     double *h_loss = nullptr;                           // pinned
@@ -1071,6 +1075,8 @@ extern "C" int az_trainer_create(az_context *ctx, int max_batch, int blocks, az_
     rc |= dev_alloc(&t->fsum, L * 2 * F);
     rc |= dev_alloc(&t->bsum, L * 2 * F);
     rc |= dev_alloc(&t->loss, 4);
+    rc |= dev_alloc(&t->d_offsets, (size_t)max_batch);
+    rc |= dev_alloc(&t->d_meta, (size_t)max_batch);
     rc |= dev_alloc(&t->d_feats, (size_t)max_batch * AZ_FEATURES);
     rc |= dev_alloc(&t->d_pol, (size_t)max_batch * AZ_LOGITS);
     rc |= dev_alloc(&t->d_val, (size_t)max_batch);
@@ -1092,7 +1098,7 @@ extern "C" void az_trainer_destroy(az_trainer *t)
     if (!t) return;
     cudaStreamSynchronize(t->ctx->stream);
     void *bufs[] = {t->theta, t->mom, t->grad, t->moving, t->mean_rstd, t->img_f, t->img_b, t->act, t->dz, t->z, t->h32, t->d_h, t->d_y,
-                    t->fsum, t->bsum, t->loss, t->wg_partial, t->d_feats, t->d_pol, t->d_val, t->d_logits, t->d_values_out};
+                    t->fsum, t->bsum, t->loss, t->wg_partial, t->d_plies, t->d_offsets, t->d_meta, t->d_feats, t->d_pol, t->d_val, t->d_logits, t->d_values_out};
     for (void *p : bufs) cudaFree(p);
     if (t->h_loss) cudaFreeHost(t->h_loss);
     for (cudaEvent_t e : t->ev)
@@ -1133,20 +1139,12 @@ extern "C" int az_trainer_load(az_trainer *t, const float *packed, size_t count)
     return AZ_OK;
 }
 
-// network.train(minibatch, learning_rate) (model.py:116-127, train.py:154-155).  losses = {policy, value, regularisation} of
-// THIS minibatch before the update, as the reference's loss tensors would evaluate in the same session call.
-extern "C" int az_trainer_step(az_trainer *t, const int8_t *features, const float *policies, const float *values, int n, float learning_rate, float *losses)
+namespace {
+// everything of a step after the minibatch has been staged in d_feats / d_pol / d_val (stream-ordered)
+int step_staged(az_trainer *t, int n, float learning_rate, float *losses, const char *who)
 {
-    int rc = check_batch(t, features, policies, values, n, "az_trainer_step");
-    if (rc) return rc;
-    AZ_REQUIRE(std::isfinite(learning_rate) && learning_rate >= 0.f, AZ_ERR_ARG, "az_trainer_step: learning rate %g", (double)learning_rate);
     cudaStream_t s = t->ctx->stream;
-    const size_t L = (size_t)t->layers;
-    AZ_CUDA(cudaMemsetAsync(t->grad, 0, t->count * sizeof(float), s));
-    AZ_CUDA(cudaMemsetAsync(t->fsum, 0, L * 2 * F * sizeof(double), s));
-    AZ_CUDA(cudaMemsetAsync(t->bsum, 0, L * 2 * F * sizeof(double), s));
-    AZ_CUDA(cudaMemsetAsync(t->loss, 0, 4 * sizeof(double), s));
-    if ((rc = stage_batch(t, features, policies, values, n))) return rc;
+    int rc;
     AZ_CUDA(cudaEventRecord(t->ev[0], s));
     if ((rc = forward(t, n, true, false))) return rc;
     if ((rc = backward(t, n))) return rc;
@@ -1160,8 +1158,75 @@ extern "C" int az_trainer_step(az_trainer *t, const int8_t *features, const floa
     AZ_CUDA(cudaEventElapsedTime(&t->last_step_ms, t->ev[0], t->ev[1]));
     t->steps++;
     if (losses) { losses[0] = (float)t->h_loss[0]; losses[1] = (float)t->h_loss[1]; losses[2] = (float)t->h_loss[2]; }
-    for (int i = 0; i < 3; ++i) AZ_REQUIRE(std::isfinite(t->h_loss[i]), AZ_ERR_STATE, "az_trainer_step: loss term %d is not finite (diverged)", i);
+    for (int i = 0; i < 3; ++i) AZ_REQUIRE(std::isfinite(t->h_loss[i]), AZ_ERR_STATE, "%s: loss term %d is not finite (diverged)", who, i);
     return AZ_OK;
+}
+
+int zero_step_accumulators(az_trainer *t)
+{
+    cudaStream_t s = t->ctx->stream;
+    const size_t L = (size_t)t->layers;
+    AZ_CUDA(cudaMemsetAsync(t->grad, 0, t->count * sizeof(float), s));
+    AZ_CUDA(cudaMemsetAsync(t->fsum, 0, L * 2 * F * sizeof(double), s));
+    AZ_CUDA(cudaMemsetAsync(t->bsum, 0, L * 2 * F * sizeof(double), s));
+    AZ_CUDA(cudaMemsetAsync(t->loss, 0, 4 * sizeof(double), s));
+    return AZ_OK;
+}
+}  // namespace
+
+// network.train(minibatch, learning_rate) (model.py:116-127, train.py:154-155).  losses = {policy, value, regularisation} of
+// THIS minibatch before the update, as the reference's loss tensors would evaluate in the same session call.
+extern "C" int az_trainer_step(az_trainer *t, const int8_t *features, const float *policies, const float *values, int n, float learning_rate, float *losses)
+{
+    int rc = check_batch(t, features, policies, values, n, "az_trainer_step");
+    if (rc) return rc;
+    AZ_REQUIRE(std::isfinite(learning_rate) && learning_rate >= 0.f, AZ_ERR_ARG, "az_trainer_step: learning rate %g", (double)learning_rate);
+    if ((rc = zero_step_accumulators(t))) return rc;
+    if ((rc = stage_batch(t, features, policies, values, n))) return rc;
+    return step_staged(t, n, learning_rate, losses, "az_trainer_step");
+}
+
+// The games a run trains on, as the binary ply table of az_samples_extract (train_data.pack_entries): uploaded ONCE and kept
+// on the device (train.py:105-110 loads its games once, too).
+extern "C" int az_trainer_set_games(az_trainer *t, const uint32_t *plies, size_t ply_words)
+{
+    AZ_REQUIRE(t && plies && ply_words >= 6, AZ_ERR_ARG, "az_trainer_set_games: bad argument");
+    AZ_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    if (t->d_plies) cudaFree(t->d_plies);
+    t->d_plies = nullptr;
+    int rc = dev_alloc(&t->d_plies, ply_words, false);
+    if (rc) return rc;
+    t->h_plies.assign(plies, plies + ply_words);
+    AZ_CUDA(cudaMemcpy(t->d_plies, plies, ply_words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return AZ_OK;
+}
+
+// One training step on the samples (offsets, meta) of the resident games -- az_samples_extract's sample description
+// (get_sample_from_entries, train.py:43-77) -- without a host round trip: the extraction kernel writes the minibatch
+// straight into the trainer's input buffers.
+extern "C" int az_trainer_step_picks(az_trainer *t, const uint64_t *offsets, const uint32_t *meta, int n, float learning_rate, float *losses)
+{
+    AZ_REQUIRE(t && offsets && meta, AZ_ERR_ARG, "az_trainer_step_picks: null argument");
+    AZ_REQUIRE(t->loaded, AZ_ERR_STATE, "az_trainer_step_picks: no weights loaded (az_trainer_load)");
+    AZ_REQUIRE(t->d_plies, AZ_ERR_STATE, "az_trainer_step_picks: no games loaded (az_trainer_set_games)");
+    AZ_REQUIRE(n >= 2 && n <= t->max_batch, AZ_ERR_ARG, "az_trainer_step_picks: batch of %d boards, this trainer takes 2..%d", n, t->max_batch);
+    AZ_REQUIRE(std::isfinite(learning_rate) && learning_rate >= 0.f, AZ_ERR_ARG, "az_trainer_step_picks: learning rate %g", (double)learning_rate);
+    const size_t words = t->h_plies.size();
+    for (int i = 0; i < n; ++i) {               // a record must lie inside the table, entries included (as in az_samples_extract)
+        AZ_REQUIRE(offsets[i] + 6 <= words, AZ_ERR_ARG, "az_trainer_step_picks: sample %d points outside the ply table", i);
+        const size_t need = ((meta[i] >> 6) & 1u) ? 6 + 2 * (size_t)(t->h_plies[offsets[i] + 4] >> 16) : 6;
+        AZ_REQUIRE(offsets[i] + need <= words, AZ_ERR_ARG, "az_trainer_step_picks: sample %d has a truncated record", i);
+        const int result = (int)((meta[i] >> 1) & 3u);
+        AZ_REQUIRE(result == 1 || result == 2, AZ_ERR_ARG, "az_trainer_step_picks: sample %d has result %d", i, result);
+    }
+    cudaStream_t s = t->ctx->stream;
+    int rc;
+    if ((rc = zero_step_accumulators(t))) return rc;
+    AZ_CUDA(cudaMemcpyAsync(t->d_offsets, offsets, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaMemcpyAsync(t->d_meta, meta, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if ((rc = az_samples_extract_dev(t->ctx, t->d_plies, t->d_offsets, t->d_meta, n, t->d_feats, t->d_pol, t->d_val))) return rc;
+    t->launches++;
+    return step_staged(t, n, learning_rate, losses, "az_trainer_step_picks");
 }
 
 // run_on_samples(policy_loss.eval / value_loss.eval) (model.py:129-142, train.py:141-142): is_training = False, so the

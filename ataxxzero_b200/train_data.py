@@ -98,6 +98,47 @@ def draw(packed, n, rng=random):
     return picks
 
 
+def _flat(packed):
+    """Per-game arrays for the vectorised draw (built once per PackedGames)."""
+    if getattr(packed, "_flat_cache", None) is None:
+        n_plies = np.array([len(o) for o in packed.offsets], dtype=np.int64)
+        start = np.concatenate([[0], np.cumsum(n_plies)[:-1]]).astype(np.int64)
+        packed._flat_cache = {
+            "n_plies": n_plies, "start": start,
+            "offsets": np.array([w for o in packed.offsets for w in o], dtype=np.uint64),
+            "is_pass": np.array([p for ps in packed.is_pass for p in ps], dtype=bool),
+            "results": np.array(packed.results, dtype=np.uint32),
+            "has_dists": np.array(packed.has_dists, dtype=np.uint32),
+            "random_ply": np.array([-1 if r is None else int(r) for r in packed.random_ply], dtype=np.int64),
+        }
+    return packed._flat_cache
+
+
+def draw_arrays(packed, n, rng):
+    """``draw`` for a whole minibatch at once with a NumPy ``Generator``: the same distribution (uniform game, uniform ply of
+    it or ``random_ply + 1``, passes redrawn, uniform symmetry; train.py:44-52,59), returned as the ``(offsets uint64 [n],
+    meta uint32 [n])`` sample description ``az_samples_extract`` / ``az_trainer_step_picks`` take."""
+    f = _flat(packed)
+    offsets = np.empty(n, dtype=np.uint64)
+    meta = np.empty(n, dtype=np.uint32)
+    have = 0
+    while have < n:
+        m = (n - have) + (n - have) // 8 + 16
+        g = rng.integers(0, len(packed), size=m)
+        ply = rng.integers(0, f["n_plies"][g])
+        rp = f["random_ply"][g]
+        ply = np.where(rp >= 0, rp + 1, ply)
+        sym = rng.integers(0, 8, size=m).astype(np.uint32)
+        idx = f["start"][g] + ply
+        keep = np.nonzero(~f["is_pass"][idx])[0][:n - have]
+        k = len(keep)
+        g, ply, sym, idx = g[keep], ply[keep], sym[keep], idx[keep]
+        offsets[have:have + k] = f["offsets"][idx]
+        meta[have:have + k] = (ply & 1).astype(np.uint32) | (f["results"][g] << 1) | (sym << 3) | (f["has_dists"][g] << 6)
+        have += k
+    return offsets, meta
+
+
 def extract(ctx, packed, picks):
     n = len(picks)
     offsets = np.zeros(max(n, 1), dtype=np.uint64)

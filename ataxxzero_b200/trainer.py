@@ -14,6 +14,8 @@ register("az_trainer_create", C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)])
 register("az_trainer_destroy", None, [_vp])
 register("az_trainer_load", C.c_int, [_vp, _vp, C.c_size_t])
 register("az_trainer_step", C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_float, _vp])
+register("az_trainer_set_games", C.c_int, [_vp, _vp, C.c_size_t])
+register("az_trainer_step_picks", C.c_int, [_vp, _vp, _vp, C.c_int, C.c_float, _vp])
 register("az_trainer_eval", C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp])
 register("az_trainer_export", C.c_int, [_vp, _vp, C.c_size_t])
 register("az_trainer_launches", C.c_ulonglong, [_vp])
@@ -56,6 +58,22 @@ class Trainer:
         f, p, v, n = _batch_arrays(features, policies, values)
         losses = np.zeros(3, dtype=np.float32)
         check(lib().az_trainer_step(self._h, _vp(f.ctypes.data), _vp(p.ctypes.data), _vp(v.ctypes.data), n, float(learning_rate), _vp(losses.ctypes.data)))
+        return float(losses[0]), float(losses[1]), float(losses[2])
+
+    def set_games(self, packed):
+        """The games this run samples from (``train_data.pack_entries``): uploaded once, kept on the device."""
+        words = np.ascontiguousarray(packed.words, dtype=np.uint32)
+        check(lib().az_trainer_set_games(self._h, _vp(words.ctypes.data), words.size))
+
+    def train_picks(self, offsets, meta, learning_rate):
+        """One step on samples of the resident games (``train_data.draw_arrays``): sample extraction and the step run
+        back to back on the device, nothing but the 12 bytes per sample of its description crosses the bus."""
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        m = np.ascontiguousarray(meta, dtype=np.uint32)
+        if o.shape != m.shape or o.ndim != 1:
+            raise ValueError("offsets %r and meta %r must be equally long vectors" % (o.shape, m.shape))
+        losses = np.zeros(3, dtype=np.float32)
+        check(lib().az_trainer_step_picks(self._h, _vp(o.ctypes.data), _vp(m.ctypes.data), len(o), float(learning_rate), _vp(losses.ctypes.data)))
         return float(losses[0]), float(losses[1]), float(losses[2])
 
     def losses(self, features, policies, values, outputs=False):

@@ -248,6 +248,12 @@ int az_trainer_load(az_trainer *trainer, const float *packed, size_t count);
  * regularisation} of this minibatch before the update. */
 int az_trainer_step(az_trainer *trainer, const int8_t *features, const float *policies, const float *values, int n, float learning_rate,
                     float *losses);
+/* The games of a training run as az_samples_extract's binary ply table, uploaded once and kept on the device (train.py:105-110
+ * loads its games once); az_trainer_step_picks then runs one step on the samples (offsets, meta) -- az_samples_extract's sample
+ * description, get_sample_from_entries (train.py:43-77) -- with no host round trip: the extraction kernel writes the minibatch
+ * straight into the trainer's input buffers. */
+int az_trainer_set_games(az_trainer *trainer, const uint32_t *plies, size_t ply_words);
+int az_trainer_step_picks(az_trainer *trainer, const uint64_t *offsets, const uint32_t *meta, int n, float learning_rate, float *losses);
 /* run_on_samples(policy_loss.eval / value_loss.eval) (train.py:141-142): is_training = False (moving statistics), any n.
  * losses = {policy, value}; logits [n][833] and values_out [n] are optional (NULL to skip). */
 int az_trainer_eval(az_trainer *trainer, const int8_t *features, const float *policies, const float *values, int n, float *losses, float *logits,

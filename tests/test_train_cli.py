@@ -69,6 +69,31 @@ def test_loss_definition_and_sampling_goldens(tmp_path):
     assert abs(float(pl) - want_pl) < 1e-5 and abs(float(vl) - want_vl) < 1e-6 and abs(float(reg) - want_reg) < 1e-7
 
 
+def test_vectorised_draw_follows_the_sampling_rules():
+    """train_data.draw_arrays (one NumPy call per minibatch) against train.py:44-52: only plies of the table, never a pass,
+    ``random_ply + 1`` when the record names one, every symmetry, and the same meta word ``extract`` builds for that pick."""
+    from ataxxzero_b200 import train_data
+    g = load_golden("train_samples_golden.json")
+    entries = [dict(e) for e in g["entries"]]
+    entries[1] = dict(entries[1], random_ply=3)
+    packed = train_data.pack_entries(entries)
+    offsets, meta = train_data.draw_arrays(packed, 6000, np.random.default_rng(5))
+    where = {int(packed.offsets[gi][ply]): (gi, ply) for gi in range(len(packed)) for ply in range(len(packed.offsets[gi]))}
+    seen_games, seen_sym = set(), set()
+    for off, m in zip(offsets.tolist(), meta.tolist()):
+        gi, ply = where[off]
+        assert not packed.is_pass[gi][ply]
+        if gi == 1:
+            assert ply == 4
+        sym = (m >> 3) & 7
+        assert m == (ply % 2) | (int(packed.results[gi]) << 1) | (sym << 3) | (int(packed.has_dists[gi]) << 6)
+        seen_games.add(gi)
+        seen_sym.add(sym)
+    assert seen_games == set(range(len(packed))) and seen_sym == set(range(8))
+    counts = np.bincount([where[o][0] for o in offsets.tolist()], minlength=len(packed))
+    assert counts.min() > 0.8 * 6000 / len(packed)            # uniform over games (train.py:45), not over plies
+
+
 def test_train_cli_needs_the_gpu_library(tmp_path):
     """No CPU training path: without a visible B200 the CLI stops at az_create instead of falling back."""
     import torch

@@ -169,6 +169,40 @@ def test_fixed_batch_run_follows_fp32_trajectory_and_export_round_trips(ctx, tmp
     tr.close()
 
 
+def test_resident_games_step_equals_host_minibatch_step(ctx):
+    """az_trainer_step_picks (games on the device, extraction + step back to back) == az_samples_extract to the host followed
+    by az_trainer_step on the same picks."""
+    from conftest import load_golden
+    from ataxxzero_b200 import AzError, model, train_data, trainer
+    entries = load_golden("train_samples_golden.json")["entries"]
+    packed = train_data.pack_entries(entries)
+    network = model.Network.random_init(seed=3, blocks=1)
+    a, b = trainer.Trainer(ctx, network, max_batch=64), trainer.Trainer(ctx, network, max_batch=64)
+    a.set_games(packed)
+    rng = np.random.default_rng(2)
+    for step in range(3):
+        offsets, meta = train_data.draw_arrays(packed, 64, rng)
+        la = a.train_picks(offsets, meta, learning_rate=0.01)
+        feats = np.zeros((64, 7, 7, 4), np.int8)
+        pol = np.zeros((64, 7, 7, 17), np.float32)
+        val = np.zeros((64, 1), np.float32)
+        _native = train_data._native
+        _native.check(_native.lib().az_samples_extract(ctx.handle, train_data._vp(packed.words.ctypes.data), packed.words.size, train_data._vp(offsets.ctypes.data),
+                                                       train_data._vp(meta.ctypes.data), 64, train_data._vp(feats.ctypes.data), train_data._vp(pol.ctypes.data),
+                                                       train_data._vp(val.ctypes.data)))
+        lb = b.train(feats, pol, val, learning_rate=0.01)
+        assert np.allclose(la, lb, rtol=1e-5, atol=1e-6), (step, la, lb)
+    assert np.allclose(a.debug_read("conv", 1), b.debug_read("conv", 1), rtol=1e-4, atol=1e-6)
+    bad = offsets.copy()
+    bad[5] = packed.words.size                                 # outside the table
+    with pytest.raises(AzError):
+        a.train_picks(bad, meta, learning_rate=0.01)
+    with pytest.raises(AzError):
+        b.train_picks(offsets, meta, learning_rate=0.01)       # no games loaded
+    a.close()
+    b.close()
+
+
 def test_full_size_step_and_argument_checks(ctx):
     """The reference's shape (128 filters x 12 blocks, minibatch 512): finite losses that fall over a few steps; bad calls fail."""
     from ataxxzero_b200 import AzError, model, trainer
