@@ -23,12 +23,14 @@
 //               so both operands are read MN-major straight from the same tile-blocked images (no transposes anywhere);
 //               a CTA owns three taps (three 128-column accumulators) and a range of tiles and writes its partial sums;
 //               k_wgrad_reduce adds the ranges up in a fixed order.
-//   k_bn_*      batch statistics (fp64 sums), normalise + residual + ReLU, and the two passes of the batch-norm backward.
+//   k_bn_*      normalise + residual + ReLU, and the second pass of the batch-norm backward.  The batch statistics themselves
+//               (sum z, sum z^2 forward; sum g, sum g*xhat backward; fp64 sums) are taken in the conv epilogues.
 //   k_heads     per board: policy / value heads, losses, their gradients, the gradient flowing into the tower.
 //   k_sgd       L2 term + momentum update, then k_images re-tiles the new weights into the two bf16 operand images.
 // Operands are bf16, accumulation and every statistic / master weight / momentum is fp32 (sums in fp64): the step agrees
-// with an fp32 PyTorch restatement to bf16 rounding (tests/test_train_gpu.py states the bounds).  Reductions use atomics, so
-// like the reference's TensorFlow step the result is not bit-reproducible from run to run.
+// with an fp32 PyTorch restatement to bf16 rounding (tests/test_train_gpu.py states the bounds).  The statistics and the head
+// gradients are summed with atomics, so like the reference's TensorFlow step the result is not bit-reproducible from run to
+// run.  The launches of a step are chained with programmatic dependent launch (pdl_trigger / pdl_wait).
 #include "az_net.h"
 #include "az_umma.cuh"
 
