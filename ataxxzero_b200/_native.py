@@ -6,6 +6,7 @@ Python/NumPy fallback anywhere in this package.
 """
 import ctypes as C
 import os
+import weakref
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AZ_LIB_PATH") or os.path.join(HERE, "libataxxzero.so")
@@ -106,6 +107,12 @@ class Context:
         self._h = _vp()
         check(lib().az_create(int(device), int(seed) & (2**64 - 1), C.byref(self._h)))
         self.device = device
+        self._dependents = weakref.WeakSet()         # pools / trainers created on this context: they hold pointers into it
+
+    def adopt(self, obj):
+        """Objects of the library that live on this context register here: ``close()`` closes them first, so a pool or trainer that
+        outlives its context (an exception unwinding, interpreter shutdown order) never touches freed memory."""
+        self._dependents.add(obj)
 
     @property
     def handle(self):
@@ -122,6 +129,11 @@ class Context:
 
     def close(self):
         if self._h:
+            for obj in list(self._dependents):
+                try:
+                    obj.close()
+                except Exception:
+                    pass
             lib().az_destroy(self._h)
             self._h = _vp()
 

@@ -73,6 +73,7 @@ class Pool:
         self.games = int(games)
         self._h = _vp()
         check(lib().az_pool_create(ctx.handle, C.byref(cfg), C.byref(self._h)))
+        ctx.adopt(self)
         self._features = np.zeros((self.games, 7, 7, 4), dtype=np.float32)
 
     # ---- lifecycle ----

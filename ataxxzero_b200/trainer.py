@@ -45,6 +45,7 @@ class Trainer:
         self._packed_size = network.packed().size
         self._h = _vp()
         check(lib().az_trainer_create(ctx.handle, self.max_batch, self.blocks, C.byref(self._h)))
+        ctx.adopt(self)
         self.load(network)
 
     def load(self, network):

@@ -54,10 +54,11 @@ def torch_setup(network, blocks, lr):
     return ref, net, torch.optim.SGD(net.parameters(), lr=lr, momentum=0.9), dev
 
 
-@pytest.mark.parametrize("blocks,n", [(2, 64), (1, 37)])
+@pytest.mark.parametrize("blocks,n", [(2, 64), (1, 37), (0, 2)])
 def test_one_step_matches_fp32_restatement(ctx, blocks, n):
     """Forward tensors, the three loss terms, every gradient tensor and the updated weights of ONE step; n = 37 leaves half a
-    tile empty (odd batch) and several tile ranges of the weight-gradient kernel without work."""
+    tile empty (odd batch) and leaves the weight-gradient kernel fewer tiles than ranges; (0, 2) is the smallest legal call: a
+    tower of the input conv alone, a batch of two boards."""
     import torch
     import torch.nn.functional as Fn
     from ataxxzero_b200 import model, trainer
@@ -125,8 +126,9 @@ def test_one_step_matches_fp32_restatement(ctx, blocks, n):
         w_ref = net.convs[l].weight.detach().permute(2, 3, 1, 0).cpu().numpy()
         w = tr.debug_read("conv", l)
         assert rel(w[:, :, :4, :] if l == 0 else w, w_ref) < 5e-3, l
-    mv = tr.debug_read("moving", 1)                                                     # update ops: decay 0.99, unbiased variance
-    assert rel(mv[0], net.bns[1].running_mean.cpu().numpy()) < 2e-2 and rel(mv[1], net.bns[1].running_var.cpu().numpy()) < 1e-4
+    top = layers - 1
+    mv = tr.debug_read("moving", top)                                                   # update ops: decay 0.99, unbiased variance
+    assert rel(mv[0], net.bns[top].running_mean.cpu().numpy()) < 2e-2 and rel(mv[1], net.bns[top].running_var.cpu().numpy()) < 1e-3
     tr.close()
 
 
@@ -226,3 +228,29 @@ def test_full_size_step_and_argument_checks(ctx):
     with pytest.raises(ValueError):
         trainer.Trainer(ctx, model.Network.random_init(seed=1, filters=64, blocks=1))
     tr.close()
+    # a minibatch that fills the GPU several times over (501 tiles: the 2-tile conv variant with an odd tile count, 48 ranges
+    # of 10-11 tiles in the weight-gradient kernel)
+    wide = trainer.Trainer(ctx, model.Network.random_init(seed=2, blocks=2), max_batch=1024)
+    big = synthetic_batch(1001, 5)
+    first = wide.train(*big, learning_rate=0.01)
+    for _ in range(8):
+        last = wide.train(*big, learning_rate=0.01)
+    assert all(np.isfinite(last)) and last[0] + last[1] < first[0] + first[1]
+    wide.close()
+
+
+def test_context_close_takes_its_pools_and_trainers_along(native):
+    """Objects created on a context hold pointers into it: closing the context first (an exception unwinding past a fixture,
+    interpreter shutdown order) must close them, not leave them to touch freed memory when they are collected later."""
+    import gc
+    import ataxxzero_b200
+    from ataxxzero_b200 import model, search, trainer
+    c = ataxxzero_b200.Context(device=0, seed=3)
+    tr = trainer.Trainer(c, model.Network.random_init(seed=1, blocks=1), max_batch=8)
+    pool = search.Pool(c, 2, 16, eval_mode=search.EVAL_EXTERNAL)
+    c.close()
+    assert not tr._h and not pool._h
+    with pytest.raises(ataxxzero_b200.AzError):
+        tr.train(*synthetic_batch(8, 1), learning_rate=0.01)
+    del tr, pool
+    gc.collect()
