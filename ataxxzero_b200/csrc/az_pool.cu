@@ -25,6 +25,7 @@ void aztree_launch_release(const PoolDev &P, const DoneEntry *d_done, int n, cud
 void aztree_launch_features(const az_position *d_pos, int n, float *d_out, cudaStream_t s);
 void aztree_launch_gather(const PoolDev &P, const DoneEntry *d_done, const uint32_t *d_offsets, int n, uint32_t *d_out, cudaStream_t s);
 void aztree_launch_debug_gamma(double alpha, uint64_t seed, int n, double *d_out, cudaStream_t s);
+void aztree_launch_debug_exp(const float *d_x, int n, double *d_out, cudaStream_t s);
 void aztree_launch_debug_sample(const int32_t *d_visits, int L, int N, uint64_t seed, int n, int32_t *d_out, cudaStream_t s);
 
 // A pool is split into GROUPS of games, each with its own tree memory, request batch and CUDA stream.  One group on the
@@ -1021,6 +1022,21 @@ extern "C" int az_debug_gamma(az_context *ctx, double alpha, uint64_t seed, int 
     aztree_launch_debug_gamma(alpha, seed, n, ctx->scratch[0].as<double>(), ctx->stream);
     ctx->launches++;
     AZ_CUDA(cudaMemcpyAsync(out, ctx->scratch[0].ptr, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    AZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+// out[2i] = the tick kernel's straight-line exponential of x[i], out[2i+1] = exp((double)x[i]) (must be bit-identical)
+extern "C" int az_debug_exp(az_context *ctx, const float *x, int n, double *out)
+{
+    AZ_REQUIRE(ctx && x && out && n > 0, AZ_ERR_ARG, "az_debug_exp: bad argument");
+    AZ_REQUIRE(ctx->scratch[0].reserve(sizeof(float) * (size_t)n) == 0 && ctx->scratch[1].reserve(2 * sizeof(double) * (size_t)n) == 0,
+               AZ_ERR_CUDA, "scratch alloc");
+    AZ_CUDA(cudaMemcpyAsync(ctx->scratch[0].ptr, x, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    aztree_launch_debug_exp(ctx->scratch[0].as<float>(), n, ctx->scratch[1].as<double>(), ctx->stream);
+    ctx->launches++;
+    AZ_CUDA(cudaMemcpyAsync(out, ctx->scratch[1].ptr, 2 * sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     AZ_CUDA(cudaStreamSynchronize(ctx->stream));
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;

@@ -24,7 +24,32 @@ def _lib():
     lib.az_debug_gamma.argtypes = [C.c_void_p, C.c_double, C.c_uint64, C.c_int, C.c_void_p]
     lib.az_debug_sample_moves.restype = C.c_int
     lib.az_debug_sample_moves.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_void_p]
+    lib.az_debug_exp.restype = C.c_int
+    lib.az_debug_exp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     return lib
+
+
+def test_straight_line_exp_is_the_library_exp(ctx):
+    """The softmax numerators (self_play_client.cpp:210-214) come from a written-out copy of CUDA's exp(double) fast path
+    (az_tree.cu exp_inline, interleaved with the sequential sums): bit-identical to exp() on 4 M floats -- the logit
+    range, every binade up to the range limit, the limit itself, and values beyond it (which take the library call) --
+    and within 1 ulp of the host's exp(), the function the reference calls."""
+    from ataxxzero_b200 import _native
+    rng = np.random.default_rng(5)
+    x = np.concatenate([
+        rng.normal(0, 3, 1 << 21), rng.uniform(-708, 708, 1 << 20), rng.uniform(-30, 30, 1 << 19),
+        (rng.uniform(1, 2, 1 << 18) * 2.0 ** rng.integers(-40, 10, 1 << 18) * rng.choice([-1, 1], 1 << 18)),
+        np.array([0.0, -0.0, 707.99994, -707.99994, 708.0, -708.0, 709.5, -745.0, 800.0, -800.0, 1e-30, -1e-30, 88.7, -103.9,
+                  np.inf, -np.inf, np.nan]),
+    ]).astype(np.float32)
+    out = np.empty((len(x), 2), np.float64)
+    _native.check(_lib().az_debug_exp(ctx.handle, C.c_void_p(x.ctypes.data), len(x), C.c_void_p(out.ctypes.data)))
+    a, b = out[:, 0].view(np.uint64), out[:, 1].view(np.uint64)
+    assert np.array_equal(a, b), "first mismatch at x = %r" % x[np.nonzero(a != b)[0][:4]]
+    finite = np.isfinite(x) & (np.abs(x) < 700)
+    host = np.exp(x[finite].astype(np.float64))
+    ulp = np.abs(out[finite, 1].view(np.int64) - host.view(np.int64))
+    assert ulp.max() <= 1
 
 
 def test_gamma_sampler_distribution(ctx):
