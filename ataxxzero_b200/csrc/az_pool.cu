@@ -8,6 +8,10 @@
 #include "az_tree.cuh"
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <charconv>
 #include <chrono>
 #include <cstdlib>
@@ -54,13 +58,40 @@ struct Group {
     std::vector<Game> h_games;
     // CUDA events around the tree and the net kernel of EVERY tick between two drains: tree_seconds / net_seconds are sums
     // of measured launches, not extrapolations
-    std::vector<cudaEvent_t> ev;          // [kTicksPerDrain][3]
+    // Two sets, used alternately: the set of the batch that just ran is read out AFTER the next batch has been launched,
+    // so the ~100 cudaEventElapsedTime calls never sit between two batches with the GPU idle.
+    std::vector<cudaEvent_t> ev[2];       // [kTicksPerDrain][3] each
+    int ev_ticks[2] = {0, 0};             // ticks recorded in the set and not yet read out
+    int ev_cur = 0;
     double trace_gap_ms = 0;
     uint64_t trace_n = 0;
 };
 
+// Finished games leave the device as packed binary records; turning them into the reference's JSON lines (sorted-key
+// objects, one std::map per ply) costs the host ~0.3 ms per game.  A writer thread does that, so the thread that launches
+// kernels goes straight back to launching.  flush() returns once every queued record is in the file (and reports a write
+// error); the entry points call it before they return or close the file.
+struct RecordJob {
+    FILE *out = nullptr;
+    std::vector<uint32_t> words;          // the drained records, back to back
+    std::vector<DoneEntry> done;
+    std::vector<uint32_t> offsets;        // word offset of every record in `words`
+};
+struct RecordWriter {
+    std::thread worker;
+    std::mutex m;
+    std::condition_variable cv, idle_cv;
+    std::deque<RecordJob> jobs;
+    bool busy = false, stop = false, failed = false;
+    void push(RecordJob &&job);
+    bool flush();                         // false: a write failed since the last flush
+    void shutdown();
+    void run();
+};
+
 struct az_pool {
     az_context *ctx = nullptr;
+    RecordWriter writer;
     az_pool_config cfg{};
     std::vector<Group> groups;
     std::vector<int> group_size;          // games per group (sums to cfg.games)
@@ -83,6 +114,8 @@ struct az_pool {
 };
 
 namespace {
+
+void read_events(az_pool *pool, int set);
 
 template <typename T>
 int dev_alloc(T **p, size_t count, bool zero = true)
@@ -197,6 +230,58 @@ std::string record_to_json(const uint32_t *rec, int words, int plies, int result
     return "{\"boards\":" + boards + "],\"dists\":" + dists + "],\"moves\":" + moves + "]" + random_ply + ",\"result\":" + std::to_string(result) + "}";
 }
 
+}  // namespace
+
+void RecordWriter::run()
+{
+    std::unique_lock<std::mutex> lock(m);
+    for (;;) {
+        cv.wait(lock, [&] { return stop || !jobs.empty(); });
+        if (jobs.empty()) return;                          // stop requested and nothing left
+        RecordJob job = std::move(jobs.front());
+        jobs.pop_front();
+        busy = true;
+        lock.unlock();
+        bool ok = true;
+        for (size_t i = 0; i < job.done.size() && ok; ++i) {
+            const DoneEntry &d = job.done[i];
+            const std::string line = record_to_json(job.words.data() + job.offsets[i], d.words, d.plies, d.result, d.random_ply);
+            ok = fwrite(line.data(), 1, line.size(), job.out) == line.size() && fputc('\n', job.out) != EOF;
+        }
+        if (ok) ok = fflush(job.out) == 0;                 // whole lines only, flushed once per drain (:641-642 flushes per game)
+        lock.lock();
+        busy = false;
+        if (!ok) failed = true;
+        if (jobs.empty()) idle_cv.notify_all();
+    }
+}
+void RecordWriter::push(RecordJob &&job)
+{
+    std::lock_guard<std::mutex> lock(m);
+    if (!worker.joinable()) worker = std::thread([this] { run(); });
+    jobs.push_back(std::move(job));
+    cv.notify_one();
+}
+bool RecordWriter::flush()
+{
+    std::unique_lock<std::mutex> lock(m);
+    idle_cv.wait(lock, [&] { return jobs.empty() && !busy; });
+    const bool ok = !failed;
+    failed = false;
+    return ok;
+}
+void RecordWriter::shutdown()
+{
+    {
+        std::lock_guard<std::mutex> lock(m);
+        stop = true;
+        cv.notify_all();
+    }
+    if (worker.joinable()) worker.join();
+}
+
+namespace {
+
 // Copy out a group's finished games, append them to `out` (may be null: records are dropped), release the buffers.
 // The records are packed into one staging buffer on the device and cross PCIe in ONE copy per drain.
 int drain_finished(az_pool *pool, Group &grp, FILE *out, int64_t *games_written, bool copy_payload = true)
@@ -227,15 +312,16 @@ int drain_finished(az_pool *pool, Group &grp, FILE *out, int64_t *games_written,
             AZ_CUDA(cudaMemcpyAsync(grp.h_stage, grp.d_stage, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost, s));
             AZ_CUDA(cudaStreamSynchronize(s));
             pool->d2h_bytes += sizeof(uint32_t) * (uint64_t)words;
-            for (int i = first; i < last && out; ++i) {
-                const DoneEntry &d = grp.h_done[i];
-                const std::string line = record_to_json(grp.h_stage + grp.h_offsets[i], d.words, d.plies, d.result, d.random_ply);
-                if (fwrite(line.data(), 1, line.size(), out) != line.size() || fputc('\n', out) == EOF)
-                    return az_fail(AZ_ERR_IO, "short write to the game file");
+            if (out) {                                    // JSON and file I/O happen on the writer thread
+                RecordJob job;
+                job.out = out;
+                job.words.assign(grp.h_stage, grp.h_stage + words);
+                job.done.assign(grp.h_done + first, grp.h_done + last);
+                job.offsets.assign(grp.h_offsets + first, grp.h_offsets + last);
+                pool->writer.push(std::move(job));
             }
             first = last;
         }
-        if (out) fflush(out);                             // whole lines only, flushed once per drain (:641-642 flushes per game)
     }
     for (int i = 0; i < n; ++i) {
         pool->written_games++;
@@ -259,7 +345,8 @@ void free_group(Group &grp)
     if (grp.h_done) cudaFreeHost(grp.h_done);
     if (grp.h_offsets) cudaFreeHost(grp.h_offsets);
     if (grp.h_stage) cudaFreeHost(grp.h_stage);
-    for (auto &e : grp.ev)
+    for (auto &set : grp.ev)
+      for (auto &e : set)
         if (e) cudaEventDestroy(e);
     if (grp.own_stream && grp.stream) cudaStreamDestroy(grp.stream);
     grp = Group();
@@ -381,6 +468,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : (cfg->games < 64 ? (1 << 20) : 48);
         D.seed = cfg->seed;
         D.tick_cycles = getenv("AZ_TICK_CYCLES") ? atoi(getenv("AZ_TICK_CYCLES")) : 0;
+        D.prefetch = getenv("AZ_TREE_PREFETCH") ? atoi(getenv("AZ_TREE_PREFETCH")) : 8;
         D.force_slow = getenv("AZ_TREE_FORCE_SLOW") ? atoi(getenv("AZ_TREE_FORCE_SLOW")) : 0;
         D.one_random_move = (cfg->auto_play && cfg->one_random_move) ? 1 : 0;
         D.rec_cap_words = rec_cap_words;
@@ -428,16 +516,18 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
             cudaMallocHost(&grp.h_offsets, sizeof(uint32_t) * 2 * G) != cudaSuccess ||
             cudaMallocHost(&grp.h_stage, sizeof(uint32_t) * grp.stage_words) != cudaSuccess) { rc = az_fail(AZ_ERR_CUDA, "az_pool_create: pinned host alloc"); break; }
         grp.h_games.resize(G);
-        grp.ev.assign(3 * kTicksPerDrain, nullptr);
-        for (auto &e : grp.ev)
-            if (cudaEventCreate(&e) != cudaSuccess) rc = az_fail(AZ_ERR_CUDA, "az_pool_create: event");
+        for (auto &set : grp.ev) {
+            set.assign(3 * kTicksPerDrain, nullptr);
+            for (auto &e : set)
+                if (cudaEventCreate(&e) != cudaSuccess) rc = az_fail(AZ_ERR_CUDA, "az_pool_create: event");
+        }
         if (n_groups > 1) {
             if (cudaStreamCreateWithFlags(&grp.stream, cudaStreamNonBlocking) != cudaSuccess) { rc = az_fail(AZ_ERR_CUDA, "az_pool_create: stream"); break; }
             grp.own_stream = true;
         } else {
             grp.stream = ctx->stream;
         }
-        if (getenv("AZ_POOL_PROFILE")) rc |= dev_alloc(&D.prof, G * 8);
+        if (getenv("AZ_POOL_PROFILE")) rc |= dev_alloc(&D.prof, G * 16);
         aztree_launch_init_all(D, start, grp.stream);
         pool->launches++;
     }
@@ -453,15 +543,17 @@ extern "C" void az_pool_destroy(az_pool *pool)
 {
     if (!pool) return;
     cudaStreamSynchronize(pool->ctx->stream);
+    pool->writer.flush();
+    pool->writer.shutdown();
     for (Group &grp : pool->groups) {
         if (grp.stream) cudaStreamSynchronize(grp.stream);
         if (grp.dev.prof) {              // per-phase cycles, accumulated over every tick: mean and worst game
-            std::vector<unsigned long long> h((size_t)grp.dev.G * 8);
+            std::vector<unsigned long long> h((size_t)grp.dev.G * 16);
             cudaMemcpy(h.data(), grp.dev.prof, h.size() * 8, cudaMemcpyDeviceToHost);
             const char *names[6] = {"populate", "backup", "descent", "expand", "make_move", "total"};
             for (int ph = 0; ph < 6; ++ph) {
                 double sum = 0, mx = 0;
-                for (int g = 0; g < grp.dev.G; ++g) { sum += (double)h[(size_t)g * 8 + ph]; mx = std::max(mx, (double)h[(size_t)g * 8 + ph]); }
+                for (int g = 0; g < grp.dev.G; ++g) { sum += (double)h[(size_t)g * 16 + ph]; mx = std::max(mx, (double)h[(size_t)g * 16 + ph]); }
                 fprintf(stderr, "[az_pool profile] %-9s mean %.1f kcycles/tick/game, worst game %.1f kcycles/tick (%llu ticks)\n", names[ph],
                         sum / grp.dev.G / std::max<uint64_t>(pool->ticks, 1) / 1e3, mx / std::max<uint64_t>(pool->ticks, 1) / 1e3,
                         (unsigned long long)pool->ticks);
@@ -470,12 +562,31 @@ extern "C" void az_pool_destroy(az_pool *pool)
             std::vector<double> start, finish;
             unsigned long long t0 = ~0ull;
             for (int g = 0; g < grp.dev.G; ++g)
-                if (h[(size_t)g * 8 + 6]) t0 = std::min(t0, h[(size_t)g * 8 + 6]);
+                if (h[(size_t)g * 16 + 6]) t0 = std::min(t0, h[(size_t)g * 16 + 6]);
+            std::vector<std::pair<double, int>> order;
             for (int g = 0; g < grp.dev.G; ++g)
-                if (h[(size_t)g * 8 + 6]) {
-                    start.push_back((double)(h[(size_t)g * 8 + 6] - t0) * 1e-3);
-                    finish.push_back((double)(h[(size_t)g * 8 + 7] - t0) * 1e-3);
+                if (h[(size_t)g * 16 + 6]) {
+                    start.push_back((double)(h[(size_t)g * 16 + 6] - t0) * 1e-3);
+                    finish.push_back((double)(h[(size_t)g * 16 + 7] - t0) * 1e-3);
+                    order.push_back({finish.back(), g});
                 }
+            // what the games of each finish-time band did in that tick (cycles per phase, steps, tree levels)
+            std::sort(order.begin(), order.end());
+            const double bands[6] = {0.0, 0.25, 0.5, 0.75, 0.9, 0.97};
+            for (int b = 0; b < 6 && !order.empty(); ++b) {
+                const size_t lo = (size_t)(bands[b] * order.size()), hi = b == 5 ? order.size() : (size_t)(bands[b + 1] * order.size());
+                double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, waiting = 0;
+                for (size_t i = lo; i < hi; ++i) {
+                    const unsigned long long *q = &h[(size_t)order[i].second * 16 + 8];
+                    for (int j = 0; j < 7; ++j) acc[j] += (double)q[j];
+                    waiting += q[7] == 1 ? 1 : 0;
+                }
+                const double n = (double)std::max<size_t>(hi - lo, 1);
+                fprintf(stderr, "[az_pool profile] last tick, finish %5.1f..%5.1f us (%4zu games): populate %5.1f backup %4.1f descent %5.1f expand %4.1f "
+                                "sum of all %5.1f kcycles | steps %.2f levels %.1f | requested an evaluation %.0f%%\n",
+                        order[lo].first, order[hi - 1].first, hi - lo, acc[0] / n / 1e3, acc[1] / n / 1e3, acc[2] / n / 1e3, acc[3] / n / 1e3,
+                        acc[4] / n / 1e3, acc[5] / n, acc[6] / n, 100.0 * waiting / n);
+            }
             if (!finish.empty()) {
                 std::sort(start.begin(), start.end());
                 std::sort(finish.begin(), finish.end());
@@ -501,6 +612,8 @@ extern "C" int az_pool_stats_get(az_pool *pool, az_pool_stats *out)
     AZ_REQUIRE(pool && out, AZ_ERR_ARG, "az_pool_stats_get: null argument");
     int rc = sync_all(pool);
     if (rc) return rc;
+    read_events(pool, 0);                          // every batch has completed: bring the timing sums up to date
+    read_events(pool, 1);
     az_pool_stats s{};
     for (Group &grp : pool->groups) {
         AZ_CUDA(cudaMemcpy(grp.h_games.data(), grp.dev.games, sizeof(Game) * grp.dev.G, cudaMemcpyDeviceToHost));
@@ -801,37 +914,59 @@ namespace {
 // the tick instead of ~105), but a net CTA can only move onto an SM once most of that SM's games are done, the games still
 // running next to it slow down 1.8x (last finish 173 us instead of 97), and the SMs hosting them start their two CTAs last
 // -- with three 170-us unit passes per CTA nothing can be rebalanced at that granularity, so the kernel ends when it did.
-int run_ticks(az_pool *pool, FILE *out, bool copy_records, int ticks, int64_t *games)
+// read out the event set `set` of every group (its batch has completed) into the pool's timing sums
+void read_events(az_pool *pool, int set)
 {
-    int rc = AZ_OK;
-    const size_t ng = pool->groups.size();
-    for (int t = 0; t < ticks && rc == AZ_OK; ++t) {
-        for (size_t gi = 0; gi < ng && rc == AZ_OK; ++gi) {
-            Group &grp = pool->groups[gi];
-            cudaEventRecord(grp.ev[3 * t], grp.stream);
-            rc = launch_tree(pool, grp);
-            cudaEventRecord(grp.ev[3 * t + 1], grp.stream);
-            if (rc == AZ_OK) rc = launch_net(pool, grp);
-            cudaEventRecord(grp.ev[3 * t + 2], grp.stream);
-        }
-        pool->ticks++;
-    }
-    if (rc) return rc;
-    for (Group &grp : pool->groups)
-        if ((rc = drain_finished(pool, grp, out, games, copy_records))) return rc;
-    if ((rc = sync_all(pool))) return rc;
-    for (Group &grp : pool->groups)
-        for (int t = 0; t < ticks; ++t) {
+    for (Group &grp : pool->groups) {
+        const std::vector<cudaEvent_t> &ev = grp.ev[set];
+        for (int t = 0; t < grp.ev_ticks[set]; ++t) {
             float a = 0.f, b = 0.f, c = 0.f;
-            if (cudaEventElapsedTime(&a, grp.ev[3 * t], grp.ev[3 * t + 1]) != cudaSuccess ||
-                cudaEventElapsedTime(&b, grp.ev[3 * t + 1], grp.ev[3 * t + 2]) != cudaSuccess) continue;
+            if (cudaEventElapsedTime(&a, ev[3 * t], ev[3 * t + 1]) != cudaSuccess || cudaEventElapsedTime(&b, ev[3 * t + 1], ev[3 * t + 2]) != cudaSuccess) continue;
             pool->tree_seconds += a * 1e-3;
             pool->net_seconds += b * 1e-3;
             pool->tick_seconds += (a + b) * 1e-3;
             if (&grp == &pool->groups[0]) pool->timed_ticks++;
-            if (t > 0 && cudaEventElapsedTime(&c, grp.ev[3 * t - 1], grp.ev[3 * t]) == cudaSuccess) { grp.trace_gap_ms += c; grp.trace_n++; }
+            if (t > 0 && cudaEventElapsedTime(&c, ev[3 * t - 1], ev[3 * t]) == cudaSuccess) { grp.trace_gap_ms += c; grp.trace_n++; }
         }
+        grp.ev_ticks[set] = 0;
+    }
+}
+
+// everything a caller may look at after an entry point returns: timing sums complete, every record in its file
+int finish_batches(az_pool *pool)
+{
+    read_events(pool, 0);
+    read_events(pool, 1);
+    if (!pool->writer.flush()) return az_fail(AZ_ERR_IO, "short write to the game file");
     return AZ_OK;
+}
+
+int run_ticks(az_pool *pool, FILE *out, bool copy_records, int ticks, int64_t *games)
+{
+    int rc = AZ_OK;
+    const size_t ng = pool->groups.size();
+    const int set = pool->groups[0].ev_cur;
+    for (int t = 0; t < ticks && rc == AZ_OK; ++t) {
+        for (size_t gi = 0; gi < ng && rc == AZ_OK; ++gi) {
+            Group &grp = pool->groups[gi];
+            cudaEventRecord(grp.ev[set][3 * t], grp.stream);
+            rc = launch_tree(pool, grp);
+            cudaEventRecord(grp.ev[set][3 * t + 1], grp.stream);
+            if (rc == AZ_OK) rc = launch_net(pool, grp);
+            cudaEventRecord(grp.ev[set][3 * t + 2], grp.stream);
+        }
+        pool->ticks++;
+    }
+    if (rc) return rc;
+    for (Group &grp : pool->groups) {
+        grp.ev_ticks[set] = ticks;
+        grp.ev_cur = set ^ 1;
+    }
+    // the previous batch finished before this one was launched: its events are read while the GPU works on this one
+    read_events(pool, set ^ 1);
+    for (Group &grp : pool->groups)
+        if ((rc = drain_finished(pool, grp, out, games, copy_records))) return rc;
+    return sync_all(pool);
 }
 }  // namespace
 
@@ -859,8 +994,10 @@ extern "C" int az_selfplay_run(az_pool *pool, const char *output_path, int64_t t
         if (max_seconds > 0 && elapsed >= max_seconds) break;
         if ((pool->ticks & 1023) < (uint64_t)kTicksPerDrain && (rc = check_game_errors(pool))) break;
     }
+    const int frc = finish_batches(pool);         // before the file is closed: the writer thread may still hold records
     if (out) fclose(out);
     if (rc) return rc;
+    if (frc) return frc;
     if ((rc = check_game_errors(pool))) return rc;
     if (stats_out) return az_pool_stats_get(pool, stats_out);
     return AZ_OK;
@@ -883,8 +1020,10 @@ extern "C" int az_selfplay_ticks(az_pool *pool, const char *output_path, int64_t
         rc = run_ticks(pool, out, out != nullptr, chunk, &games);
         done += chunk;
     }
+    const int frc = finish_batches(pool);         // before the file is closed: the writer thread may still hold records
     if (out) fclose(out);
     if (rc) return rc;
+    if (frc) return frc;
     if ((rc = check_game_errors(pool))) return rc;
     if (stats_out) return az_pool_stats_get(pool, stats_out);
     return AZ_OK;
@@ -981,7 +1120,7 @@ extern "C" int get_workload(void)
     }
     std::memcpy(g_legacy.fill[h], st.data(), sizeof(float) * AZ_FEATURES * (size_t)have);
     int64_t dummy = 0;
-    if (drain_finished(pool, pool->groups[0], g_legacy.out, &dummy)) legacy_die("drain");
+    if (drain_finished(pool, pool->groups[0], g_legacy.out, &dummy) || !pool->writer.flush()) legacy_die("drain");
     g_legacy.waiting[h] = true;
     g_legacy.next ^= 1;
     return h;

@@ -159,6 +159,8 @@ struct PoolDev {
     int32_t req_cap;         // requests the net kernel serves per tick
     uint32_t tick_id;        // increments with every tick
     int32_t one_random_move; // the reference's compile-time ONE_RANDOM_MOVE variant of generate_game (self_play_client.cpp:24,515-552)
+    int32_t prefetch;        // a level pulls the children of a node with at most this many edges into L2 while it selects
+                             // (default 8, AZ_TREE_PREFETCH=0 switches it off)
     int32_t force_slow;      // test knob (AZ_TREE_FORCE_SLOW=1): resolve every candidate by the full scan
     unsigned long long *prof;   // AZ_POOL_PROFILE=1: [G][8] clock cycles per phase of the last tick (debug aid, normally nullptr)
 };
