@@ -26,7 +26,38 @@ def _lib():
     lib.az_debug_sample_moves.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_void_p]
     lib.az_debug_exp.restype = C.c_int
     lib.az_debug_exp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.az_debug_div.restype = C.c_int
+    lib.az_debug_div.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     return lib
+
+
+def test_paired_division_is_the_library_division(ctx):
+    """select_action's two divisions per edge (sqrt(1+N)/(1+n) and W/n, self_play_client.cpp:316-323) run as one
+    interleaved block (az_tree.cu div_pair): bit-identical to __ddiv_rn on 2 M operand pairs -- PUCT-shaped operands
+    (square roots of counts over counts, score sums over counts), zero and tiny numerators, huge and subnormal quotients
+    (those take the fallback) -- and equal to the host's IEEE division."""
+    from ataxxzero_b200 import _native
+    rng = np.random.default_rng(11)
+    n = 1 << 20
+    counts = rng.integers(1, 1 << 23, n).astype(np.float64)
+    small = rng.integers(1, 900, n).astype(np.float64)
+    a1 = np.sqrt(1.0 + rng.integers(0, 1 << 23, n))
+    b1 = np.where(rng.random(n) < 0.7, 1.0 + small, 1.0 + counts)
+    b2 = np.where(rng.random(n) < 0.7, small, counts)
+    a2 = b2 * rng.random(n)                                    # a total score between 0 and n
+    a2[rng.random(n) < 0.05] = 0.0                             # an edge that only ever lost
+    m = 1 << 16                                                # the corners of the fast path
+    ea = np.concatenate([2.0 ** rng.uniform(-1074, -960, m), 2.0 ** rng.uniform(900, 1023, m), rng.uniform(0, 1, m), np.zeros(m)])
+    eb = np.concatenate([rng.integers(1, 1 << 23, 2 * m).astype(np.float64), 2.0 ** rng.uniform(-900, 900, 2 * m)])
+    a1 = np.concatenate([a1, ea]); b1 = np.concatenate([b1, eb])
+    a2 = np.concatenate([a2, ea[::-1]]); b2 = np.concatenate([b2, eb[::-1]])
+    inp = np.ascontiguousarray(np.stack([a1, b1, a2, b2], axis=1))
+    out = np.empty_like(inp)
+    _native.check(_lib().az_debug_div(ctx.handle, C.c_void_p(inp.ctypes.data), len(inp), C.c_void_p(out.ctypes.data)))
+    bits = out.view(np.uint64)
+    assert np.array_equal(bits[:, 0], bits[:, 2]) and np.array_equal(bits[:, 1], bits[:, 3])
+    with np.errstate(all="ignore"):
+        assert np.array_equal((a1 / b1).view(np.uint64), bits[:, 2]) and np.array_equal((a2 / b2).view(np.uint64), bits[:, 3])
 
 
 def test_straight_line_exp_is_the_library_exp(ctx):
