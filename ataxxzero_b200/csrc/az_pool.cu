@@ -61,11 +61,9 @@ struct Group {
     // of measured launches, not extrapolations
     // Two sets, used alternately: the set of the batch that just ran is read out AFTER the next batch has been launched,
     // so the ~100 cudaEventElapsedTime calls never sit between two batches with the GPU idle.
-    std::vector<cudaEvent_t> ev[2];       // [kTicksPerDrain][3] each
+    std::vector<cudaEvent_t> ev[2];       // [1 + 2 * kTicksPerDrain] each
     int ev_ticks[2] = {0, 0};             // ticks recorded in the set and not yet read out
     int ev_cur = 0;
-    double trace_gap_ms = 0;
-    uint64_t trace_n = 0;
 };
 
 // Finished games leave the device as packed binary records; turning them into the reference's JSON lines (sorted-key
@@ -518,7 +516,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
             cudaMallocHost(&grp.h_stage, sizeof(uint32_t) * grp.stage_words) != cudaSuccess) { rc = az_fail(AZ_ERR_CUDA, "az_pool_create: pinned host alloc"); break; }
         grp.h_games.resize(G);
         for (auto &set : grp.ev) {
-            set.assign(3 * kTicksPerDrain, nullptr);
+            set.assign(1 + 2 * kTicksPerDrain, nullptr);
             for (auto &e : set)
                 if (cudaEventCreate(&e) != cudaSuccess) rc = az_fail(AZ_ERR_CUDA, "az_pool_create: event");
         }
@@ -600,9 +598,6 @@ extern "C" void az_pool_destroy(az_pool *pool)
             cudaFree(grp.dev.prof);
             grp.dev.prof = nullptr;
         }
-        if (grp.trace_n && getenv("AZ_POOL_TRACE"))
-            fprintf(stderr, "[az_pool trace] group@%d: idle gap between ticks %.4f ms (mean over %llu ticks)\n", grp.first_game,
-                    grp.trace_gap_ms / grp.trace_n, (unsigned long long)grp.trace_n);
         free_group(grp);
     }
     delete pool;
@@ -919,15 +914,16 @@ namespace {
 void read_events(az_pool *pool, int set)
 {
     for (Group &grp : pool->groups) {
+        // ev[0]: before the batch; ev[1 + 2t] / ev[2 + 2t]: behind the tree / the net kernel of tick t.  A kernel's time runs from the
+        // event behind its predecessor, so the launch gap in front of it is part of it.
         const std::vector<cudaEvent_t> &ev = grp.ev[set];
         for (int t = 0; t < grp.ev_ticks[set]; ++t) {
-            float a = 0.f, b = 0.f, c = 0.f;
-            if (cudaEventElapsedTime(&a, ev[3 * t], ev[3 * t + 1]) != cudaSuccess || cudaEventElapsedTime(&b, ev[3 * t + 1], ev[3 * t + 2]) != cudaSuccess) continue;
+            float a = 0.f, b = 0.f;
+            if (cudaEventElapsedTime(&a, ev[2 * t], ev[2 * t + 1]) != cudaSuccess || cudaEventElapsedTime(&b, ev[2 * t + 1], ev[2 * t + 2]) != cudaSuccess) continue;
             pool->tree_seconds += a * 1e-3;
             pool->net_seconds += b * 1e-3;
             pool->tick_seconds += (a + b) * 1e-3;
             if (&grp == &pool->groups[0]) pool->timed_ticks++;
-            if (t > 0 && cudaEventElapsedTime(&c, ev[3 * t - 1], ev[3 * t]) == cudaSuccess) { grp.trace_gap_ms += c; grp.trace_n++; }
         }
         grp.ev_ticks[set] = 0;
     }
@@ -947,14 +943,14 @@ int run_ticks(az_pool *pool, FILE *out, bool copy_records, int ticks, int64_t *g
     int rc = AZ_OK;
     const size_t ng = pool->groups.size();
     const int set = pool->groups[0].ev_cur;
+    for (size_t gi = 0; gi < ng; ++gi) cudaEventRecord(pool->groups[gi].ev[set][0], pool->groups[gi].stream);
     for (int t = 0; t < ticks && rc == AZ_OK; ++t) {
         for (size_t gi = 0; gi < ng && rc == AZ_OK; ++gi) {
             Group &grp = pool->groups[gi];
-            cudaEventRecord(grp.ev[set][3 * t], grp.stream);
             rc = launch_tree(pool, grp);
-            cudaEventRecord(grp.ev[set][3 * t + 1], grp.stream);
+            cudaEventRecord(grp.ev[set][2 * t + 1], grp.stream);
             if (rc == AZ_OK) rc = launch_net(pool, grp);
-            cudaEventRecord(grp.ev[set][3 * t + 2], grp.stream);
+            cudaEventRecord(grp.ev[set][2 * t + 2], grp.stream);
         }
         pool->ticks++;
     }
