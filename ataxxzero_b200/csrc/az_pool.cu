@@ -30,7 +30,7 @@ void aztree_launch_features(const az_position *d_pos, int n, float *d_out, cudaS
 void aztree_launch_gather(const PoolDev &P, const DoneEntry *d_done, const uint32_t *d_offsets, int n, uint32_t *d_out, cudaStream_t s);
 void aztree_launch_debug_gamma(double alpha, uint64_t seed, int n, double *d_out, cudaStream_t s);
 void aztree_launch_debug_exp(const float *d_x, int n, double *d_out, cudaStream_t s);
-void aztree_launch_debug_div(const double *d_in, int n, double *d_out, cudaStream_t s);
+void aztree_launch_debug_div(const double *d_in, int n, int puct, double *d_out, cudaStream_t s);
 void aztree_launch_debug_sample(const int32_t *d_visits, int L, int N, uint64_t seed, int n, int32_t *d_out, cudaStream_t s);
 
 // A pool is split into GROUPS of games, each with its own tree memory, request batch and CUDA stream.  One group on the
@@ -1179,13 +1179,14 @@ extern "C" int az_debug_exp(az_context *ctx, const float *x, int n, double *out)
 }
 
 // in[4i..4i+3] = a1, b1, a2, b2; out[4i..4i+3] = the tick kernel's paired division (q1, q2), then a1/b1 and a2/b2 by the library
-extern "C" int az_debug_div(az_context *ctx, const double *in, int n, double *out)
+// puct != 0: the variant select_action runs (operands must be PUCT-shaped: a1 in [1, 2^12], b counts, a2 a score sum or 0)
+extern "C" int az_debug_div(az_context *ctx, const double *in, int n, int puct, double *out)
 {
     AZ_REQUIRE(ctx && in && out && n > 0, AZ_ERR_ARG, "az_debug_div: bad argument");
     const size_t bytes = 4 * sizeof(double) * (size_t)n;
     AZ_REQUIRE(ctx->scratch[0].reserve(bytes) == 0 && ctx->scratch[1].reserve(bytes) == 0, AZ_ERR_CUDA, "scratch alloc");
     AZ_CUDA(cudaMemcpyAsync(ctx->scratch[0].ptr, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    aztree_launch_debug_div(ctx->scratch[0].as<double>(), n, ctx->scratch[1].as<double>(), ctx->stream);
+    aztree_launch_debug_div(ctx->scratch[0].as<double>(), n, puct, ctx->scratch[1].as<double>(), ctx->stream);
     ctx->launches++;
     AZ_CUDA(cudaMemcpyAsync(out, ctx->scratch[1].ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     AZ_CUDA(cudaStreamSynchronize(ctx->stream));

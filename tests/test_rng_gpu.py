@@ -27,7 +27,7 @@ def _lib():
     lib.az_debug_exp.restype = C.c_int
     lib.az_debug_exp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.az_debug_div.restype = C.c_int
-    lib.az_debug_div.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.az_debug_div.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return lib
 
 
@@ -46,6 +46,16 @@ def test_paired_division_is_the_library_division(ctx):
     b2 = np.where(rng.random(n) < 0.7, small, counts)
     a2 = b2 * rng.random(n)                                    # a total score between 0 and n
     a2[rng.random(n) < 0.05] = 0.0                             # an edge that only ever lost
+    # the variant the kernel runs on exactly these operand shapes (only the score sum is range-checked there)
+    puct_in = np.ascontiguousarray(np.stack([a1, b1, a2, b2], axis=1))
+    tiny = rng.random(n) < 0.02                                # one visit whose value was (v+1)/2 of a float v just above -1
+    puct_in[tiny, 2] = (np.float32(-1.0) + np.float32(2.0) ** rng.integers(-24, -1, tiny.sum()).astype(np.float32) + 1.0).astype(np.float64) / 2.0
+    puct_out = np.empty_like(puct_in)
+    _native.check(_lib().az_debug_div(ctx.handle, C.c_void_p(puct_in.ctypes.data), len(puct_in), 1, C.c_void_p(puct_out.ctypes.data)))
+    pb = puct_out.view(np.uint64)
+    assert np.array_equal(pb[:, 0], pb[:, 2]) and np.array_equal(pb[:, 1], pb[:, 3])
+    assert np.array_equal((puct_in[:, 0] / puct_in[:, 1]).view(np.uint64), pb[:, 0])
+    assert np.array_equal((puct_in[:, 2] / puct_in[:, 3]).view(np.uint64), pb[:, 1])
     m = 1 << 16                                                # the corners of the fast path
     ea = np.concatenate([2.0 ** rng.uniform(-1074, -960, m), 2.0 ** rng.uniform(900, 1023, m), rng.uniform(0, 1, m), np.zeros(m)])
     eb = np.concatenate([rng.integers(1, 1 << 23, 2 * m).astype(np.float64), 2.0 ** rng.uniform(-900, 900, 2 * m)])
@@ -53,7 +63,7 @@ def test_paired_division_is_the_library_division(ctx):
     a2 = np.concatenate([a2, ea[::-1]]); b2 = np.concatenate([b2, eb[::-1]])
     inp = np.ascontiguousarray(np.stack([a1, b1, a2, b2], axis=1))
     out = np.empty_like(inp)
-    _native.check(_lib().az_debug_div(ctx.handle, C.c_void_p(inp.ctypes.data), len(inp), C.c_void_p(out.ctypes.data)))
+    _native.check(_lib().az_debug_div(ctx.handle, C.c_void_p(inp.ctypes.data), len(inp), 0, C.c_void_p(out.ctypes.data)))
     bits = out.view(np.uint64)
     assert np.array_equal(bits[:, 0], bits[:, 2]) and np.array_equal(bits[:, 1], bits[:, 3])
     with np.errstate(all="ignore"):
