@@ -586,6 +586,13 @@ extern "C" void az_pool_destroy(az_pool *pool)
                         order[lo].first, order[hi - 1].first, hi - lo, acc[0] / n / 1e3, acc[1] / n / 1e3, acc[2] / n / 1e3, acc[3] / n / 1e3,
                         acc[4] / n / 1e3, acc[5] / n, acc[6] / n, 100.0 * waiting / n);
             }
+            // the stragglers one by one: the tick ends with the last of them
+            for (size_t i = order.size() > 12 ? order.size() - 12 : 0; i < order.size(); ++i) {
+                const unsigned long long *q = &h[(size_t)order[i].second * 16 + 8];
+                fprintf(stderr, "[az_pool profile] straggler game %5d finished %5.1f us: populate %5.1f backup %4.1f descent %5.1f expand %4.1f "
+                                "all %5.1f kcycles | steps %llu levels %llu status %llu\n",
+                        order[i].second, order[i].first, q[0] / 1e3, q[1] / 1e3, q[2] / 1e3, q[3] / 1e3, q[4] / 1e3, q[5], q[6], q[7]);
+            }
             if (!finish.empty()) {
                 std::sort(start.begin(), start.end());
                 std::sort(finish.begin(), finish.end());

@@ -33,6 +33,10 @@ def main():
             continue
         if hdr is None or not r[0].strip().isdigit():
             continue                                  # SASS rows carry no line number
+        if len(r) > len(hdr):
+            # a source line with unescaped quotes (inline asm) splits into extra cells: the counters are the LAST cells
+            extra = len(r) - len(hdr)
+            r = [r[0], ",".join(r[1:2 + extra])] + r[2 + extra:]
         try:
             samples, inst = int(float(r[i_samples] or 0)), int(float(r[i_inst] or 0))
         except (ValueError, IndexError):
