@@ -464,9 +464,14 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         }
         // the level budget trims the tail of a tick over thousands of games; a handful of trees has no tail to trim, and a
         // suspended descent would cost it a whole (empty) net launch
-        D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : (cfg->games < 64 ? (1 << 20) : 48);
+        // Capped pools (thousands of games, the net launch is full anyway) bound a game's share of a tick in CLOCKS -- 105 k, a
+        // budget a game spends on whatever it has to do (a game that resumes a suspended descent has no evaluation to consume
+        // and gets further) -- with a wide level bound behind it; +0.6 % over 48 levels in three A/B sweeps
+        // (profiles/r02_tree_phases.txt).  Pools of a few hundred games keep the level budget alone.
+        const bool capped = D.cap < D.G;
+        D.levels_per_tick = getenv("AZ_LEVELS_PER_TICK") ? atoi(getenv("AZ_LEVELS_PER_TICK")) : (cfg->games < 64 ? (1 << 20) : capped ? 200 : 48);
         D.seed = cfg->seed;
-        D.tick_cycles = getenv("AZ_TICK_CYCLES") ? atoi(getenv("AZ_TICK_CYCLES")) : 0;
+        D.tick_cycles = getenv("AZ_TICK_CYCLES") ? atoi(getenv("AZ_TICK_CYCLES")) : (capped && !getenv("AZ_LEVELS_PER_TICK") ? 105000 : 0);
         D.prefetch = getenv("AZ_TREE_PREFETCH") ? atoi(getenv("AZ_TREE_PREFETCH")) : 8;
         D.force_slow = getenv("AZ_TREE_FORCE_SLOW") ? atoi(getenv("AZ_TREE_FORCE_SLOW")) : 0;
         D.one_random_move = (cfg->auto_play && cfg->one_random_move) ? 1 : 0;
