@@ -208,7 +208,8 @@ int az_pool_play(az_pool *pool, int game, az_move move);
 
 /* Self-play generation (generate_game + Worker::thread_main, self_play_client.cpp:508-645): runs until
  * `target_games` finished games have been appended to `output_path` as reference-format JSON lines,
- * `target_positions` plies were recorded or `max_seconds` passed (0 = no limit on that axis). */
+ * `target_positions` plies were recorded or `max_seconds` passed (0 = no limit on that axis).  The lines are formatted and
+ * written by a background thread while the kernels run; every record of a finished game is in the file when the call returns. */
 int az_selfplay_run(az_pool *pool, const char *output_path, int64_t target_games, int64_t target_positions,
                     double max_seconds, az_pool_stats *stats_out);
 
