@@ -38,6 +38,7 @@ void aztree_launch_debug_sample(const int32_t *d_visits, int L, int N, uint64_t 
 // only) let the tree kernel of one group run under the net kernel of another; that overlap is opt-in because it measured
 // SLOWER on B200: a tree kernel that shares SMs with the net kernel's weight stream takes ~2.2x longer.
 const int kTicksPerDrain = 32;
+const int kEventPeriod = 1024, kEventWindow = 256;    // CUDA events on the first 256 ticks of every 1024 (run_ticks)
 
 struct Group {
     PoolDev dev{};
@@ -64,6 +65,7 @@ struct Group {
     std::vector<cudaEvent_t> ev[2];       // [1 + 2 * kTicksPerDrain] each
     int ev_ticks[2] = {0, 0};             // ticks recorded in the set and not yet read out
     int ev_cur = 0;
+    unsigned long long *d_timed_evals = nullptr;      // evaluations served by the event-timed net launches (counted on the device)
 };
 
 // Finished games leave the device as packed binary records; turning them into the reference's JSON lines (sorted-key
@@ -100,6 +102,7 @@ struct az_pool {
     double net_seconds = 0.0, tree_seconds = 0.0;     // sums over every launch of the self-play loop (CUDA events)
     double tick_seconds = 0.0;                        // every tick, first event to last
     uint64_t timed_ticks = 0;                         // ticks behind the three sums
+    uint64_t timed_evals_host = 0;                    // evaluations of the timed launches that closed a batch (counted after its sync)
     uint64_t written_games = 0, written_positions = 0, d2h_bytes = 0;
 
     Group &group_of(int game, int *local)
@@ -337,7 +340,7 @@ void free_group(Group &grp)
     PoolDev &D = grp.dev;
     void *ptrs[] = {D.nodes, D.games, D.path, D.gstack, D.req_pos, D.req_game, D.req_count, D.logits, D.values, D.cache_tag,
                     D.cache_exps, D.cache_tot, D.cache_val, D.req_out, D.records,
-                    D.done, D.done_count, grp.d_done_snapshot, grp.d_status, grp.d_features, grp.d_offsets, grp.d_stage};
+                    D.done, D.done_count, grp.d_done_snapshot, grp.d_status, grp.d_timed_evals, grp.d_features, grp.d_offsets, grp.d_stage};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (grp.h_counts) cudaFreeHost(grp.h_counts);
@@ -514,6 +517,7 @@ extern "C" int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_poo
         grp.stage_words = (size_t)D.rec_cap_words * (cfg->auto_play ? std::min<size_t>(2 * G, 64) : 1);
         rc |= dev_alloc(&grp.d_stage, grp.stage_words, false);
         rc |= dev_alloc(&grp.d_status, 4);
+        rc |= dev_alloc(&grp.d_timed_evals, 1);
         rc |= dev_alloc(&grp.d_features, G * AZ_FEATURES);
         if (rc) break;
         if (cudaMallocHost(&grp.h_counts, 16 * sizeof(int32_t)) != cudaSuccess || cudaMallocHost(&grp.h_done, sizeof(DoneEntry) * 2 * G) != cudaSuccess ||
@@ -643,6 +647,12 @@ extern "C" int az_pool_stats_get(az_pool *pool, az_pool_stats *out)
     s.tree_seconds = pool->tree_seconds;
     s.tick_seconds = pool->tick_seconds;
     s.timed_ticks = pool->timed_ticks;
+    s.timed_evals = pool->timed_evals_host;
+    for (Group &grp : pool->groups) {
+        unsigned long long n = 0;
+        AZ_CUDA(cudaMemcpy(&n, grp.d_timed_evals, sizeof(n), cudaMemcpyDeviceToHost));
+        s.timed_evals += n;
+    }
     *out = s;
     return AZ_OK;
 }
@@ -955,27 +965,42 @@ int run_ticks(az_pool *pool, FILE *out, bool copy_records, int ticks, int64_t *g
     int rc = AZ_OK;
     const size_t ng = pool->groups.size();
     const int set = pool->groups[0].ev_cur;
-    for (size_t gi = 0; gi < ng; ++gi) cudaEventRecord(pool->groups[gi].ev[set][0], pool->groups[gi].stream);
+    // Which launches carry events: a timing event between two kernels costs ~3 us of GPU time (the front end cannot prepare
+    // the next launch behind it: 0.579 against 0.572 ms per tick with and without them), so the events sit on a CONTIGUOUS
+    // window of kEventWindow ticks out of every kEventPeriod -- every tree and net launch inside a window is bracketed, and
+    // the evaluations those net launches served are counted on the device (PoolDev::timed_evals), nothing is extrapolated.
+    // AZ_POOL_EVENT_WINDOW=<ticks> changes the window (>= the period: every tick, 0: none).
+    static const int window = getenv("AZ_POOL_EVENT_WINDOW") ? atoi(getenv("AZ_POOL_EVENT_WINDOW")) : kEventWindow;
+    const bool timed = (int)(pool->ticks % kEventPeriod) < window;
+    for (size_t gi = 0; gi < ng && timed; ++gi) cudaEventRecord(pool->groups[gi].ev[set][0], pool->groups[gi].stream);
     for (int t = 0; t < ticks && rc == AZ_OK; ++t) {
         for (size_t gi = 0; gi < ng && rc == AZ_OK; ++gi) {
             Group &grp = pool->groups[gi];
+            grp.dev.timed_evals = (timed && t > 0) ? grp.d_timed_evals : nullptr;      // tick t's tree kernel counts tick t-1's net launch
             rc = launch_tree(pool, grp);
-            cudaEventRecord(grp.ev[set][2 * t + 1], grp.stream);
+            grp.dev.timed_evals = nullptr;
+            if (timed) cudaEventRecord(grp.ev[set][2 * t + 1], grp.stream);
             if (rc == AZ_OK) rc = launch_net(pool, grp);
-            cudaEventRecord(grp.ev[set][2 * t + 2], grp.stream);
+            if (timed) cudaEventRecord(grp.ev[set][2 * t + 2], grp.stream);
         }
         pool->ticks++;
     }
     if (rc) return rc;
+    if (timed)                                    // the batch's last net launch: its request count is read behind the batch
+        for (Group &grp : pool->groups)
+            AZ_CUDA(cudaMemcpyAsync(grp.h_counts + 4, grp.dev.req_count + 2 * grp.slot, sizeof(int32_t), cudaMemcpyDeviceToHost, grp.stream));
     for (Group &grp : pool->groups) {
-        grp.ev_ticks[set] = ticks;
+        grp.ev_ticks[set] = timed ? ticks : 0;
         grp.ev_cur = set ^ 1;
     }
     // the previous batch finished before this one was launched: its events are read while the GPU works on this one
     read_events(pool, set ^ 1);
     for (Group &grp : pool->groups)
         if ((rc = drain_finished(pool, grp, out, games, copy_records))) return rc;
-    return sync_all(pool);
+    if ((rc = sync_all(pool))) return rc;
+    if (timed)
+        for (Group &grp : pool->groups) pool->timed_evals_host += (uint64_t)std::min(grp.h_counts[4], grp.dev.cap);
+    return AZ_OK;
 }
 }  // namespace
 

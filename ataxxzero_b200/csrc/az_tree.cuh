@@ -162,6 +162,7 @@ struct PoolDev {
     int32_t prefetch;        // a level pulls the children of a node with at most this many edges into L2 while it selects
                              // (default 8, AZ_TREE_PREFETCH=0 switches it off)
     int32_t force_slow;      // test knob (AZ_TREE_FORCE_SLOW=1): resolve every candidate by the full scan
+    unsigned long long *timed_evals;   // non-null: the previous tick's net launch was event-timed -- add the evaluations it served
     unsigned long long *prof;   // AZ_POOL_PROFILE=1: [G][8] clock cycles per phase of the last tick (debug aid, normally nullptr)
 };
 

@@ -30,7 +30,7 @@ class PoolStats(C.Structure):
                 ("max_depth", C.c_uint64), ("kernel_launches", C.c_uint64), ("record_bytes", C.c_uint64),
                 ("net_seconds", C.c_double),
                 ("tree_seconds", C.c_double), ("levels", C.c_uint64), ("tick_seconds", C.c_double),
-                ("timed_ticks", C.c_uint64)]
+                ("timed_ticks", C.c_uint64), ("timed_evals", C.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

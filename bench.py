@@ -412,10 +412,13 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (net), from CUDA events around its launches ----
     pk, pk_kind = peaks()
-    # net_seconds / tree_seconds: CUDA events around every k_tree_tick and k_net_pair launch of the timed region, summed
+    # net_seconds / tree_seconds: CUDA events around every k_tree_tick and k_net_pair launch of the event-carrying ticks -- a
+    # contiguous window of 256 ticks out of every 1024 (a timing event between two kernels costs ~3 us of GPU time, so the other
+    # ticks run without) -- summed; timed_evals = the evaluations exactly those net launches served, counted on the device
     net_s = max(d["net_seconds"], 1e-9)
     timed = max(d.get("timed_ticks", 0), 1)
-    achieved = d["evals"] * FLOP_PER_EVAL / net_s / 1e12
+    timed_evals = d.get("timed_evals", 0)
+    achieved = timed_evals * FLOP_PER_EVAL / net_s / 1e12
     peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)))
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_net_pair"]["dram_bytes_per_launch"]
@@ -424,16 +427,19 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "k_net_pair (bf16 tcgen05 cta_group::2 tower on CTA pairs)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_note": "dram__bytes_read+write per launch from profiles/ (ncu --set full); the weights stream from L2",
-                "flop_per_launch": d["evals"] / timed * FLOP_PER_EVAL,
+                "flop_per_launch": timed_evals / timed * FLOP_PER_EVAL,
                 "peak_kind": "%s bf16_tflops_sustained (kernel timed inside a long step)" % pk_kind,
                 "net_share_of_step": d["net_seconds"] / max(d["net_seconds"] + d["tree_seconds"], 1e-9),
                 "tree_ms_per_tick": d["tree_seconds"] / timed * 1e3, "net_ms_per_tick": d["net_seconds"] / timed * 1e3,
-                "launches_timed": int(2 * timed),
-                "timing": "CUDA events around EVERY k_tree_tick and k_net_pair launch of the timed region (%d ticks, summed, not sampled)" % timed}
+                "launches_timed": int(2 * timed), "evals_timed": int(timed_evals),
+                "timing": "CUDA events around every k_tree_tick and k_net_pair launch of %d ticks (contiguous 256-tick windows, one per 1024 "
+                          "ticks of the timed region), summed; the evaluations of exactly those net launches are counted on the device; "
+                          "ticks outside the windows carry no events (an event between two kernels costs ~3 us)" % timed}
     # tree kernel: HBM roofline on SURVEY 8(d)'s algorithmic bytes of the reference algorithm (13 KB per MCTS step: every
     # child's P/W/n at every level of the selection path, the backup, 833 logits, the new node)
     tree_s = max(d["tree_seconds"], 1e-9)
-    tree_bytes = d["steps"] * TREE_BYTES_PER_STEP
+    steps_per_launch = d["steps"] / max(d["ticks"], 1)            # MCTS steps per tree launch, mean over the whole timed region
+    tree_bytes = steps_per_launch * timed * TREE_BYTES_PER_STEP      # ... times the launches that carried events
     hbm_peak = float(pk.get("hbm_gbs", 6550.0))
     try:
         tree_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_tree_tick"]["dram_bytes_per_launch"]
@@ -442,9 +448,9 @@ def run_ours(args):
     roofline["kernels"] = {
         "k_tree_tick": {"bound": "hbm", "achieved": tree_bytes / tree_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": tree_bytes / tree_s / 1e9 / hbm_peak, "traffic": tree_traffic,
-                        "algorithmic_bytes_per_step": TREE_BYTES_PER_STEP, "steps_per_launch": d["steps"] / max(d["ticks"], 1),
+                        "algorithmic_bytes_per_step": TREE_BYTES_PER_STEP, "steps_per_launch": steps_per_launch,
                         "levels_per_step": d.get("levels", 0) / max(d["steps"], 1),
-                        "us_per_level_per_game": tree_s * 1e6 / max(d["ticks"], 1) / max(d.get("levels", 0) / max(d["ticks"], 1) / games, 1e-9),
+                        "us_per_level_per_game": tree_s * 1e6 / timed / max(d.get("levels", 0) / max(d["ticks"], 1) / games, 1e-9),
                         "note": "latency-bound by design: one warp per game walks a dependent chain of tree levels; the compact node "
                                 "layout reads far fewer bytes than the reference algorithm's 13 KB per step"}}
 

@@ -171,11 +171,13 @@ typedef struct {
     uint64_t max_depth;        /* deepest selection path seen                                     */
     uint64_t kernel_launches;  /* kernels launched by the pool                                    */
     uint64_t record_bytes;     /* game-record bytes copied device -> host                         */
-    double   net_seconds;      /* device time in the net kernel: CUDA events around EVERY launch of the self-play loop, summed */
+    double   net_seconds;      /* device time in the net kernel: CUDA events around every launch of the timed ticks, summed    */
     double   tree_seconds;     /* ... and in the tree kernel                                                                  */
     uint64_t levels;           /* tree levels walked by completed selections (sum of path lengths)                            */
     double   tick_seconds;     /* tree + net of every self-play tick                                                          */
-    uint64_t timed_ticks;      /* ticks behind the three sums (az_selfplay_* only; az_pool_run does not time its ticks)       */
+    uint64_t timed_ticks;      /* ticks behind the three sums (az_selfplay_* only; az_pool_run does not time its ticks): the   */
+                               /* events sit on contiguous windows, the first 256 ticks of every 1024                          */
+    uint64_t timed_evals;      /* evaluations served by the net launches of those ticks (counted on the device)                */
 } az_pool_stats;
 
 int az_pool_create(az_context *ctx, const az_pool_config *cfg, az_pool **out);
