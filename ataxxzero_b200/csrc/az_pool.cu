@@ -583,6 +583,7 @@ extern "C" void az_pool_destroy(az_pool *pool)
             const double bands[6] = {0.0, 0.25, 0.5, 0.75, 0.9, 0.97};
             for (int b = 0; b < 6 && !order.empty(); ++b) {
                 const size_t lo = (size_t)(bands[b] * order.size()), hi = b == 5 ? order.size() : (size_t)(bands[b + 1] * order.size());
+                if (hi <= lo) continue;                    // pools of a few games: not every band has one
                 double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, waiting = 0;
                 for (size_t i = lo; i < hi; ++i) {
                     const unsigned long long *q = &h[(size_t)order[i].second * 16 + 8];
